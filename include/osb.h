@@ -1,0 +1,193 @@
+/*
+ * osb.h — C ABI of the B200-native open-set head + evaluation path ("osb" = open-set B200).
+ *
+ * One shared library (openset_imagenet_b200/csrc/libosb.so, sm_100a only) exports exactly the
+ * functions declared here.  Plain pointers and sizes only; no C++/torch types.  The reference
+ * (AIML-IfI/openset-imagenet) is pure Python and has no FFI of its own, so each entry cites the
+ * reference call site (file:line, relative to the reference root) whose arithmetic it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its comment says host;
+ *   - the caller owns all memory, including workspaces (size from the matching *_workspace_bytes);
+ *     the library never allocates or frees device memory and keeps no per-call state;  a workspace
+ *     must be zero-filled ONCE by its owner before first use, every entry leaves it reusable, and one
+ *     workspace must not be shared by calls that may run concurrently on different streams;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it, nothing synchronises, every entry is CUDA-graph capturable;
+ *   - every function returns an int status: OSB_OK or a negative OSB_ERR_*;  no exception crosses
+ *     the ABI;  osb_last_error() gives a thread-local message for the last failure;
+ *   - there is NO CPU fallback: without a compute-capability-10.x device every compute entry
+ *     returns OSB_ERR_ARCH.
+ */
+#ifndef OSB_H_
+#define OSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSB_ABI_VERSION 1
+
+/* status codes */
+#define OSB_OK             0
+#define OSB_ERR_ARG       -1   /* null pointer, negative size, misaligned pointer, bad enum        */
+#define OSB_ERR_SHAPE     -2   /* shape outside what the kernels support (message says which)      */
+#define OSB_ERR_WORKSPACE -3   /* workspace too small                                              */
+#define OSB_ERR_CUDA      -4   /* a CUDA runtime / driver call failed (message has the error name) */
+#define OSB_ERR_ARCH      -5   /* no CUDA device, or device is not sm_100                           */
+
+/* loss variants: losses.py:7-29 (entropic), train.py:343 (softmax), train.py:346-347 (garbage) */
+#define OSB_ENTROPIC 0
+#define OSB_SOFTMAX  1
+#define OSB_GARBAGE  2
+
+/* element types of logits / dlogits */
+#define OSB_F32  0
+#define OSB_BF16 1
+
+/* label types accepted by the OSCR row reduce (`gt` is float32 in the reference's npz files,
+ * train.py:212, and cast with astype(int) at util.py:100) */
+#define OSB_LABEL_I64 0
+#define OSB_LABEL_F32 1
+#define OSB_LABEL_I32 2
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         osb_abi_version(void);
+const char* osb_last_error(void);            /* host string, valid until the next failing call on this thread */
+int         osb_device_check(void);          /* OSB_OK iff the current device is compute capability 10.x */
+int         osb_sm_count(void);              /* SM count of the current device (148 on B200), <0 on error */
+
+/* ---- labels -> denominator and counts ------------------------------------------------------ *
+ * Replaces the host-synchronising label bookkeeping of losses.py:18-26 and the implicit reductions
+ * inside torch.nn.CrossEntropyLoss (train.py:343,347).
+ *   den[0]    (double)  loss denominator of THIS shard: B (entropic), #rows with y != ignore_index
+ *                       (softmax), sum_i class_w[y_i] over non-ignored rows (garbage);
+ *   counts[4] (int64)   {rows with a one-hot target, rows with the uniform negative target,
+ *                        ignored rows, rows whose label is out of range}.
+ * Out-of-range labels (reference: IndexError / device assert) never fault: they are counted in
+ * counts[3], treated as ignored rows, and poison the loss with NaN in the consumers below.
+ */
+int osb_label_stats(const int64_t* y, const float* class_w, int64_t B, int C, int variant,
+                    int64_t ignore_index, double* den, int64_t* counts,
+                    void* ws, size_t ws_bytes, void* stream);   /* ws: osb_loss_workspace_bytes(B) */
+
+/* ---- loss from materialised logits --------------------------------------------------------- *
+ * Drop-in arithmetic of EntropicOpensetLoss.__call__ (losses.py:16-29) and of the two
+ * CrossEntropyLoss configurations (train.py:343,347) when the caller already holds logits [B,C].
+ *   logits   [B, ld] of `dtype`; y [B] int64; class_w [C] float32 (garbage only, else NULL)
+ *   den      device double[1]: denominator to divide by (osb_label_stats output, or its all-reduced
+ *            sum when the batch is sharded across GPUs)
+ *   loss_num device double[1] out: sum of un-normalised row losses of this shard
+ *   loss     device float[1]  out: loss_num / den  (NaN if den == 0 or any label was out of range)
+ *   lse      device float[B]  out, nullable: row log-sum-exp (saved for backward)
+ *   row_ptgt / row_pmax / row_pmax_all / row_pred : nullable per-row outputs
+ *            softmax prob of the label column (0 when the label is not a column), max prob over the
+ *            first `valid_cols` columns (metrics.py:39), max prob over all columns and first argmax
+ *            over all columns (util.py:109-110).
+ *   dlogits  nullable [B, ldd] of `dtype`: gscale * d loss / d logits; gscale is a device float[1]
+ *            (upstream gradient, NULL = 1) so backward needs no host sync.
+ */
+size_t osb_loss_workspace_bytes(int64_t B);
+int osb_loss_from_logits(const void* logits, int dtype, int64_t ld, const int64_t* y,
+                         const float* class_w, int64_t B, int C, int variant, double unk_weight,
+                         int64_t ignore_index, const double* den, int valid_cols,
+                         double* loss_num, float* loss, float* lse,
+                         float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
+                         void* dlogits, int64_t ldd, const float* gscale,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused head: linear -> softmax statistics -> loss -> grad-logits -> dX, dW, db ---------- *
+ * Replaces model.py:23-26,37-38 (the logits linear), losses.py:16-29 / train.py:343,347 (loss),
+ * train.py:177 (softmax for confidence/OSCR, reduced to per-row statistics) and the autograd
+ * backward of all of them (train.py:138).  tcgen05/TMEM GEMMs fed by TMA; the logits live only in
+ * TMEM/registers.
+ *   x [B, K] bf16 row-major (ldx elements), w [C, K] bf16 row-major (nn.Linear layout), bias [C]
+ *   float32 or NULL.  K % 64 == 0, C <= 1024.
+ * forward : loss_num/loss/row_* as above; dz (nullable) [B, lddz] bf16 = UN-scaled grad-logits
+ *           saved for backward (lddz % 8 == 0, lddz >= C).
+ * backward: dx (nullable) [B, lddx] bf16 = g * dz @ w ; dw [C, K] float32 = g * dz^T @ x ;
+ *           db (nullable) [C] float32 = g * column sums of dz ; g = gscale[0] (device) or 1.
+ */
+size_t osb_head_workspace_bytes(int64_t B, int K, int C);
+int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
+                     const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
+                     int64_t ignore_index, const double* den, int valid_cols,
+                     double* loss_num, float* loss,
+                     float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
+                     void* dz, int64_t lddz, void* ws, size_t ws_bytes, void* stream);
+int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
+                      int64_t B, int K, int C, const float* gscale,
+                      void* dx, int64_t lddx, float* dw, float* db,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---- confidence (metrics.py:8-42) ---------------------------------------------------------- *
+ *   scores [N, ld] float32, y [N] int64.
+ *   sums[2]   (double) {sum over known rows of s[i,y_i],
+ *                       sum over rows with y == unknown_class of float32(1+offset) - max_c s[i,:valid_cols]}
+ *   counts[3] (int64)  {kn_count, neg_count, known rows whose label is >= C (reference: IndexError)}
+ * Counts are exact; sums are accumulated in double in a fixed order (bit-reproducible run to run).
+ * The division and the empty-group rule (metrics.py:29-34) are left to the caller.
+ */
+size_t osb_confidence_workspace_bytes(int64_t N);
+int osb_confidence(const float* scores, int64_t ld, const int64_t* y, int64_t N, int C,
+                   float one_plus_offset, int64_t unknown_class, int valid_cols,
+                   double* sums, int64_t* counts, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- OSCR (util.py:90-122) ----------------------------------------------------------------- *
+ * Stage A  osb_oscr_rowreduce: one pass over scores [N, ld] float32 (util.py:100-111):
+ *   keys[3*N] uint32, three segments of N order-preserving float keys, 0xFFFFFFFF where absent:
+ *     [0,N)   target score of every known row (gt >= 0)                 -> thresholds
+ *     [N,2N)  target score of known rows with argmax == gt              -> CCR counts
+ *     [2N,3N) row max of rows with gt == unk_label                      -> FPR counts
+ *   totals[4] int64 {n_known, n_correct, n_unk, n_bad (known label >= C)}
+ * Stage B  osb_oscr_sort: LSD radix sort (8-bit digits, warp-level match ranking, single-pass
+ *   chained-scan scatter) of `nseg` segments (segment s starts at keys + s*n and holds seg_len[s] <= n
+ *   keys), in place (keys_alt [nseg*n] is scratch).
+ * Stage C  osb_oscr_thresholds: unique known keys of the sorted segment 0 (np.unique, util.py:113);
+ *   taus[j] (float32) for j < n_unique, meta[0] = n_unique.  The largest is dropped by the caller
+ *   (n_thresholds = max(n_unique-1, 0)).
+ * Stage D  osb_oscr_counts: for every threshold, #correct-known > tau and #unk > tau (strict,
+ *   util.py:114,117) from the sorted segments of THIS shard: ccr_cnt/fpr_cnt int64 [n_unique].
+ * osb_oscr runs A-D on one GPU and also writes ccr/fpr = counts / totals as float64.
+ */
+size_t osb_oscr_workspace_bytes(int64_t N);
+int osb_oscr_rowreduce(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+                       int64_t unk_label, uint32_t* keys, int64_t* totals, void* stream);
+size_t osb_oscr_sort_workspace_bytes(int64_t n, int nseg);
+size_t osb_oscr_thresholds_workspace_bytes(int64_t n);
+int osb_oscr_sort(uint32_t* keys, uint32_t* keys_alt, int64_t n, int nseg,
+                  const int64_t* seg_len /* device [nseg], nullable: every segment holds n keys */,
+                  void* ws, size_t ws_bytes, void* stream);
+int osb_oscr_thresholds(const uint32_t* sorted_known, int64_t n, const int64_t* n_known,
+                        uint32_t* tau_keys, float* taus, int64_t* n_unique,
+                        void* ws, size_t ws_bytes, void* stream);
+int osb_oscr_counts(const uint32_t* tau_keys, const int64_t* n_unique,
+                    const uint32_t* sorted_correct, const int64_t* n_correct,
+                    const uint32_t* sorted_unk, const int64_t* n_unk, int64_t n,
+                    int64_t* ccr_cnt, int64_t* fpr_cnt, void* stream);
+int osb_oscr_ratios(const int64_t* ccr_cnt, const int64_t* fpr_cnt, const int64_t* n_unique,
+                    const int64_t* n_known, const int64_t* n_unk, int64_t n,
+                    double* ccr, double* fpr, void* stream);
+int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+             int64_t unk_label, float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt,
+             double* ccr, double* fpr, int64_t* meta /* [5]: n_unique, n_known, n_correct, n_unk, n_bad */,
+             void* ws, size_t ws_bytes, void* stream);
+
+/* ---- CCR@FPR (script/plot_all.py:346-352,378-384) ------------------------------------------ *
+ * For each of nq <= 16 queries q (host doubles): idx = first argmin_j |fpr[j]-q| over the
+ * n_unique[0]-1 thresholds the reference keeps (NaN counts as the minimum, like numpy.argmin).
+ * out_idx[nq] int64 (-1 when there are no thresholds), out_fpr[nq], out_ccr[nq] double (device).
+ * The 10 % acceptance rule is a host-side round() on out_fpr and stays in the Python wrapper.
+ */
+int osb_ccr_at_fpr(const double* ccr, const double* fpr, const int64_t* n_unique, int64_t n,
+                   const double* queries_host, int nq, int64_t* out_idx, double* out_fpr,
+                   double* out_ccr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSB_H_ */

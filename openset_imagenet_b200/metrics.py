@@ -1,0 +1,69 @@
+"""``metrics.confidence`` of the reference (openset_imagenet/metrics.py:8-42) on the GPU.
+
+One streaming kernel: known rows gather a single element, only rows labelled ``unknown_class`` are read
+in full, counts are exact, sums are accumulated in double in a fixed order.  The reference's other
+helpers in that file (``predict_objectosphere``, ``auc_score_*``) are dead code there (imported, never
+called) and are out of scope.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _valid_cols(C: int, last_valid_class) -> int:
+    # python slice semantics of scores[unknown, :last_valid_class] (metrics.py:39)
+    return len(range(C)[slice(None, last_valid_class)])
+
+
+def confidence_sums(scores: torch.Tensor, target_labels: torch.Tensor, offset=0., unknown_class=-1,
+                    last_valid_class=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Device-side result without a host sync: ``sums`` float64 [2] = (sum of known target scores, sum of
+    1+offset-max over negatives) and ``counts`` int64 [3] = (kn_count, neg_count, labels >= C).
+    Additive across shards (all-reduce both for a sharded validation set)."""
+    dev = L.require_cuda(scores, target_labels)
+    if scores.dim() != 2:
+        raise ValueError(f"scores must be [samples, classes], got {tuple(scores.shape)}")
+    N, Cc = scores.shape
+    if scores.dtype != torch.float32:
+        scores = scores.float()
+    if scores.stride(1) != 1 and Cc > 1:
+        scores = scores.contiguous()
+    y = target_labels
+    if y.dtype != torch.int64:
+        y = y.long()
+    y = y.contiguous()
+    if y.dim() != 1 or y.shape[0] != N:
+        raise ValueError(f"target_labels must be [samples]={N}, got {tuple(y.shape)}")
+    vc = _valid_cols(Cc, last_valid_class)
+    sums = torch.zeros(2, dtype=torch.float64, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    if N == 0:
+        return sums, counts
+    one_plus_offset = float(torch.tensor(1.0 + offset, dtype=torch.float32))   # the scalar torch would use
+    with torch.cuda.device(dev):
+        ws = L.workspace("conf", L.size("osb_confidence_workspace_bytes", N), dev)
+        L.call("osb_confidence", L.ptr(scores), scores.stride(0), L.ptr(y), N, Cc, one_plus_offset,
+               int(unknown_class), vc, L.ptr(sums), L.ptr(counts), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    return sums, counts
+
+
+def confidence(scores, target_labels, offset=0., unknown_class=-1, last_valid_class=None):
+    """Drop-in for ``openset_imagenet.metrics.confidence``.
+
+    Returns ``(kn_conf, kn_count, neg_conf, neg_count)`` as Python ``(float, int, float, int)``:
+    the mean target-class score of known samples (label >= 0 and != unknown_class) and the mean of
+    ``1 + offset - max_c scores[:, :last_valid_class]`` over samples labelled ``unknown_class``;
+    0.0 for an empty group (metrics.py:29-40).  Like the reference it raises on an empty input.
+    """
+    if scores.shape[0] == 0:
+        raise AttributeError("'int' object has no attribute 'item'")      # what sum([]).item() raises there
+    sums, counts = confidence_sums(scores, target_labels, offset, unknown_class, last_valid_class)
+    s = sums.tolist()
+    kn_count, neg_count, bad = counts.tolist()
+    if bad:
+        raise IndexError(f"{bad} known label(s) out of range for {scores.shape[1]} classes")
+    kn_conf = s[0] / kn_count if kn_count else 0.0
+    neg_conf = s[1] / neg_count if neg_count else 0.0
+    return kn_conf, kn_count, neg_conf, neg_count

@@ -1,0 +1,143 @@
+"""OSCR evaluation of the reference (openset_imagenet/util.py:90-122) and the CCR@FPR lookup of
+``plot_imagenet.py`` (script/plot_all.py:346-352,378-384) on the GPU.
+
+``calculate_oscr(gt, scores, unk_label)`` keeps the reference's signature and return type (two
+float64 numpy arrays, one entry per unique known target score except the largest) but runs as a
+streaming row reduce + radix sort + scan instead of the reference's O(U*N) Python loop; the integer
+counts behind every entry are bit-exact.  As in the reference, dropping a garbage-class column is the
+caller's job (util.py:186-187 drops it, plot_all.py:359-363 does not).
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_LABEL_TYPES = {torch.int64: L.LABEL_I64, torch.float32: L.LABEL_F32, torch.int32: L.LABEL_I32}
+
+
+@dataclass
+class OscrDeviceResult:
+    """Everything ``calculate_oscr`` computes, still on the device (no host sync has happened).
+
+    Arrays have capacity N; the first ``meta[0] - 1`` entries are the reference's output (the largest
+    unique threshold is dropped, util.py:113).  meta = [n_unique, n_known, n_correct, n_unk, n_bad].
+    """
+    taus: torch.Tensor
+    ccr_cnt: torch.Tensor
+    fpr_cnt: torch.Tensor
+    ccr: torch.Tensor
+    fpr: torch.Tensor
+    meta: torch.Tensor
+
+
+def _to_device(a, device, dtype=None) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True)
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("openset_imagenet_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def calculate_oscr_device(gt, scores, unk_label=-1, device=None) -> OscrDeviceResult:
+    """Enqueue the whole OSCR computation on the current stream; host arrays are copied in first."""
+    if isinstance(scores, torch.Tensor) and scores.is_cuda:
+        dev = scores.device
+    else:
+        dev = torch.device(device) if device is not None else default_device()
+    s = _to_device(scores, dev, torch.float32)
+    if s.dim() != 2:
+        raise ValueError(f"scores must be [samples, classes], got {tuple(s.shape)}")
+    if s.stride(1) != 1 and s.shape[1] > 1:
+        s = s.contiguous()
+    g = _to_device(gt, dev)
+    if g.dtype not in _LABEL_TYPES:
+        # anything else goes through the same truncating cast as gt.astype(int) (util.py:100)
+        g = g.to(torch.int64)
+    g = g.contiguous()
+    N, Cc = s.shape
+    if g.dim() != 1 or g.shape[0] != N:
+        raise ValueError(f"gt must be [samples]={N}, got {tuple(g.shape)}")
+    with torch.cuda.device(dev):
+        cap = max(N, 1)
+        taus = torch.empty(cap, dtype=torch.float32, device=dev)
+        ccr_cnt = torch.empty(cap, dtype=torch.int64, device=dev)
+        fpr_cnt = torch.empty(cap, dtype=torch.int64, device=dev)
+        ccr = torch.empty(cap, dtype=torch.float64, device=dev)
+        fpr = torch.empty(cap, dtype=torch.float64, device=dev)
+        meta = torch.zeros(5, dtype=torch.int64, device=dev)
+        ws = L.workspace("oscr", L.size("osb_oscr_workspace_bytes", N), dev)
+        L.call("osb_oscr", L.ptr(s), s.stride(0) if N else Cc, L.ptr(g), _LABEL_TYPES[g.dtype], N, Cc, int(unk_label),
+               L.ptr(taus), L.ptr(ccr_cnt), L.ptr(fpr_cnt), L.ptr(ccr), L.ptr(fpr), L.ptr(meta),
+               L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    return OscrDeviceResult(taus, ccr_cnt, fpr_cnt, ccr, fpr, meta)
+
+
+def calculate_oscr(gt, scores, unk_label=-1):
+    """Drop-in for ``openset_imagenet.util.calculate_oscr``.
+
+    Args:
+        gt: integer (or float, as stored in the reference's npz files) target labels [N]; numpy array or tensor.
+        scores: float array [N, C] (or [N, C+1]); numpy array, CPU tensor or CUDA tensor.
+        unk_label: label whose samples count towards the false-positive rate (-1 negatives, -2 unknowns).
+    Returns: (ccr, fpr) float64 numpy arrays.
+    """
+    r = calculate_oscr_device(gt, scores, unk_label)
+    n_unique, n_known, _, n_unk, n_bad = r.meta.tolist()
+    if n_bad:
+        raise IndexError(f"{n_bad} label(s) out of bounds for axis 1 with size {scores.shape[1]}")
+    n = max(n_unique - 1, 0)
+    ccr = r.ccr[:n].cpu().numpy()
+    fpr = r.fpr[:n].cpu().numpy()
+    if n and n_unk == 0:
+        warnings.warn("invalid value encountered in scalar divide", RuntimeWarning, stacklevel=2)
+    return ccr, fpr
+
+
+def ccr_at_fpr_device(ccr: torch.Tensor, fpr: torch.Tensor, n_unique: torch.Tensor, queries):
+    """First argmin |fpr - q| per query on the device; returns (idx int64, fpr_at, ccr_at) tensors."""
+    dev = L.require_cuda(ccr, fpr, n_unique)
+    q = (L.C.c_double * len(queries))(*[float(v) for v in queries])
+    out_idx = torch.empty(len(queries), dtype=torch.int64, device=dev)
+    out_fpr = torch.empty(len(queries), dtype=torch.float64, device=dev)
+    out_ccr = torch.empty(len(queries), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.call("osb_ccr_at_fpr", L.ptr(ccr), L.ptr(fpr), L.ptr(n_unique), ccr.numel(), q, len(queries),
+               L.ptr(out_idx), L.ptr(out_fpr), L.ptr(out_ccr), L.stream_ptr(dev))
+    return out_idx, out_fpr, out_ccr
+
+
+def ccr_at_fpr(ccr, fpr, queries=(1e-3, 1e-2, 0.1, 1.0), device=None):
+    """Numeric part of ``conf_and_ccr_table`` (script/plot_all.py:346-352,378-384).
+
+    For each query q returns ``(idx, fpr[idx], value)`` with idx = first argmin |fpr - q| and value =
+    ccr[idx], or None when ``round(100*|fpr[idx]-q|/q, 1) >= 10.0`` (printed as '---' by the reference).
+    ``ccr``/``fpr`` are the arrays ``calculate_oscr`` returned (numpy) or their device tensors.
+    """
+    if isinstance(fpr, torch.Tensor) and fpr.is_cuda:
+        dev = fpr.device
+    else:
+        dev = torch.device(device) if device is not None else default_device()
+    c = _to_device(ccr, dev, torch.float64).contiguous()
+    f = _to_device(fpr, dev, torch.float64).contiguous()
+    if f.numel() == 0:
+        raise ValueError("attempt to get argmin of an empty sequence")
+    n_unique = torch.tensor([f.numel() + 1], dtype=torch.int64, device=dev)
+    idx, f_at, c_at = ccr_at_fpr_device(c, f, n_unique, queries)
+    out = []
+    for q, i, fv, cv in zip(queries, idx.tolist(), f_at.tolist(), c_at.tolist()):
+        err = round(100 * abs(fv - q) / q, 1)
+        out.append((i, fv, None if err >= 10.0 else cv))
+    return out
