@@ -1,13 +1,823 @@
-// placeholder until the tcgen05 head lands (replaced in the next commit)
+// Fused open-set head on tcgen05 tensor cores (sm_100a).
+//
+//   head_fwd_kernel : Z = X W^T (+b) accumulated in TMEM, and an epilogue that never writes Z: online
+//                     log-softmax statistics, entropic / softmax / garbage loss, confidence statistics,
+//                     arg-max, and the un-scaled grad-logits dZ (bf16, TMA store).  Heads wider than the
+//                     512 TMEM columns (C <= 1024) run as a 2-CTA cluster that splits the classes and
+//                     exchanges the per-row softmax statistics through distributed shared memory.
+//   head_dx_kernel  : dX = g * dZ W          (persistent, double-buffered TMEM accumulators)
+//   head_dw_kernel  : dW = g * dZ^T X        (split over the batch, deterministic partial reduce)
+//
+// All operands are 128B-swizzled TMA tiles; one tile layout serves as K-major or MN-major operand
+// (tc05.cuh).  Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
+// allocator, warps 2..5 = epilogue (TMEM lane quadrant = warp % 4, one thread per accumulator row).
+//
+// Reference arithmetic: model.py:23-26,37-38 (linear), losses.py:16-29 / train.py:343,347 (losses),
+// train.py:177 + metrics.py:33-40 + util.py:109-111 (the per-row statistics), autograd of those.
 #include "osb_common.cuh"
-extern "C" size_t osb_head_workspace_bytes(int64_t, int, int) { return 0; }
-extern "C" int osb_head_forward(const void*, int64_t, const void*, const float*, const int64_t*, const float*, int64_t, int, int, int, double,
-                                int64_t, const double*, int, double*, float*, float*, float*, float*, int32_t*, void*, int64_t, void*, size_t, void*) {
-    osb::set_error("osb_head_forward: not built yet");
-    return OSB_ERR_SHAPE;
+#include "row_modes.cuh"
+#include "tc05.cuh"
+
+namespace osb {
+namespace head {
+
+using namespace osb::tc;
+
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr int BM = 128;                 // accumulator rows per tile (UMMA M)
+constexpr int BK = 64;                  // elements per 128-byte swizzle row
+constexpr int kABytes = BM * BK * 2;    // 16 KB: 128 rows x 128 B
+constexpr int kBoxBytes = 64 * BK * 2;  // 8 KB: 64 rows x 128 B
+constexpr int kStageWarpBytes = 32 * 128;   // epilogue staging: 32 rows x 128 B per warp
+constexpr int kMaxPartials = 2048;
+constexpr size_t kHeadTicketBytes = 128;
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
-extern "C" int osb_head_backward(const void*, int64_t, const void*, int64_t, const void*, int64_t, int, int, const float*, void*, int64_t,
-                                 float*, float*, void*, size_t, void*) {
-    osb::set_error("osb_head_backward: not built yet");
-    return OSB_ERR_SHAPE;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---- cluster helpers (2-CTA class split) -------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_peer_f32(uint32_t raddr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(raddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer(uint32_t raddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// pack 8 fp32 -> 8 bf16 and store one 16-byte chunk of a 128B-swizzled staging row
+__device__ __forceinline__ void stage_chunk(uint8_t* sbuf, int row, int chunk, const float* f) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
+}
+
+// =================================================================================================
+// forward: logits in TMEM -> loss, statistics, dZ
+// =================================================================================================
+struct FwdArgs {
+    const float* bias; const int64_t* y; const float* class_w;
+    int B, K, C; int variant; float t_uniform; int64_t ignore_index; const double* den; int valid_cols;
+    double* loss_num; float* loss;
+    float* row_ptgt; float* row_pmax; float* row_pmax_all; int32_t* row_pred;
+    int write_dz;
+    double* partials; unsigned int* ticket;
+};
+
+// BN: rows of one W slot (UMMA N of a full chunk); NCHUNK: chunks per CTA; CL: cluster size (class split);
+// NBUF: TMEM accumulator buffers; SA / SB: ring depths of the X tiles and the W slots.
+template <int BN, int NCHUNK, int CL, int NBUF, int SA, int SB>
+struct FwdCfg {
+    static constexpr int kSlotBytes = BN * BK * 2;
+    static constexpr int kBufCols = BN * NCHUNK;                 // accumulator columns per buffer
+    static constexpr int kTmemCols = (kBufCols * NBUF <= 128) ? 128 : (kBufCols * NBUF <= 256 ? 256 : 512);
+    static constexpr int kOffB = SA * kABytes;
+    static constexpr int kOffStage = kOffB + SB * kSlotBytes;
+    static constexpr int kOffXch = kOffStage + 4 * 2 * kStageWarpBytes;      // [2][128][8] floats
+    static constexpr int kOffBias = kOffXch + 2 * BM * 8 * 4;                // [kBufCols] floats
+    static constexpr int kOffBars = kOffBias + kBufCols * 4;
+    static constexpr int kNumBars = 2 * SA + 2 * SB + 2 * NBUF + 2;
+    static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;  // + tmem slot + alignment slack
+    static_assert(kBufCols * NBUF <= 512, "TMEM has 512 columns");
+    static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+};
+
+template <int BN, int NCHUNK, int CL, int NBUF, int SA, int SB, bool HAS_BIAS>
+__global__ void __launch_bounds__(kThreads, 1)
+head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                const __grid_constant__ CUtensorMap tm_dz, const FwdArgs a) {
+    using Cfg = FwdCfg<BN, NCHUNK, CL, NBUF, SA, SB>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::kOffB;
+    uint8_t* sStage = smem + Cfg::kOffStage;
+    float* sXch = reinterpret_cast<float*>(smem + Cfg::kOffXch);
+    float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
+    uint64_t* a_full = bars;              uint64_t* a_empty = a_full + SA;
+    uint64_t* b_full = a_empty + SA;      uint64_t* b_empty = b_full + SB;
+    uint64_t* t_full = b_empty + SB;      uint64_t* t_empty = t_full + NBUF;
+    uint64_t* x_bar = t_empty + NBUF;     // [2] statistics exchange (cluster only)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    const int n_tiles = (a.B + BM - 1) / BM;
+    const int n_kb = (a.K + BK - 1) / BK;
+    // class range of this CTA
+    const int n0 = (int)rank * (BN * NCHUNK);
+    int ncols = a.C - n0;                                 // real columns owned by this CTA
+    ncols = ncols < 0 ? 0 : (ncols > BN * NCHUNK ? BN * NCHUNK : ncols);
+    const int ncols16 = (ncols + 15) & ~15;               // UMMA N granularity
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        mbar_init(&x_bar[0], BM); mbar_init(&x_bar[1], BM);
+        fence_barrier_init();
+        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dz);
+    }
+    if (HAS_BIAS) {
+        for (int i = threadIdx.x; i < BN * NCHUNK; i += kThreads) sBias[i] = (i < ncols) ? a.bias[n0 + i] : 0.f;
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before_sync();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    const uint32_t s = ia % SA, ph = (ia / SA) & 1; ++ia;
+                    mbar_wait(&a_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&a_full[s], kABytes);
+                    tma_load_2d(sA + s * kABytes, &tm_x, &a_full[s], kb * BK, tile * BM);
+#pragma unroll
+                    for (int j = 0; j < NCHUNK; ++j) {
+                        if (j * BN < ncols16) {
+                            const uint32_t sb = ib % SB, pb = (ib / SB) & 1; ++ib;
+                            mbar_wait(&b_empty[sb], pb ^ 1);
+                            mbar_arrive_expect_tx(&b_full[sb], Cfg::kSlotBytes);
+                            tma_load_2d(sB + sb * Cfg::kSlotBytes, &tm_w, &b_full[sb], kb * BK, n0 + j * BN);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer --------------------------------
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0, it = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
+                const uint32_t buf = it % NBUF, tph = (it / NBUF) & 1;
+                mbar_wait(&t_empty[buf], tph ^ 1);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    const uint32_t s = ia % SA, ph = (ia / SA) & 1; ++ia;
+                    mbar_wait(&a_full[s], ph);
+                    const uint32_t a_addr = smem_u32(sA + s * kABytes);
+#pragma unroll
+                    for (int j = 0; j < NCHUNK; ++j) {
+                        if (j * BN < ncols16) {
+                            const int nj = (ncols16 - j * BN) < BN ? (ncols16 - j * BN) : BN;
+                            const uint32_t idesc = make_idesc_bf16(BM, nj, false, false);
+                            const uint32_t sb = ib % SB, pb = (ib / SB) & 1; ++ib;
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after_sync();
+                            const uint32_t b_addr = smem_u32(sB + sb * Cfg::kSlotBytes);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_bf16(tbase + buf * Cfg::kBufCols + j * BN, make_desc_kmajor(a_addr + k * 32),
+                                          make_desc_kmajor(b_addr + k * 32), idesc, (kb | k) != 0);
+                            umma_commit(&b_empty[sb]);
+                        }
+                    }
+                    umma_commit(&a_empty[s]);
+                }
+                umma_commit(&t_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ epilogue ----------------------------------
+        const int q = warp & 3;                         // TMEM lane quadrant of this warp
+        const int r_in_tile = q * 32 + lane;
+        uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
+        const float inv_den = (float)(1.0 / a.den[0]);
+        const float s_uniform = a.t_uniform * (float)a.C;
+        double loss_acc = 0.0;
+        uint32_t it = 0, n_stores = 0;
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
+            const uint32_t buf = it % NBUF, tph = (it / NBUF) & 1;
+            const int row = tile * BM + r_in_tile;
+            const bool row_ok = row < a.B;
+            const int64_t y = row_ok ? a.y[row] : -1;
+            RowMode rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, s_uniform);
+            if (!row_ok) { rm.mode = kRowIgnored; rm.omega = 0.f; }
+            const int y_local = (y >= n0 && y < n0 + ncols) ? (int)(y - n0) : -1;
+            mbar_wait(&t_full[buf], tph);
+            tc_fence_after_sync();
+            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * Cfg::kBufCols);
+
+            // ---- sweep A: online softmax statistics over this CTA's columns ----
+            float m = -INFINITY, s = 0.f, sumz = 0.f, zy = 0.f, mv = -INFINITY, best = -INFINITY;
+            int am = 0x7fffffff;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + c0, v);
+                tmem_ld_wait();
+                float z[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    z[i] = __uint_as_float(v[i]);
+                    if (HAS_BIAS) z[i] += sBias[c0 + i];
+                }
+                if (c0 + 32 > ncols) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (c0 + i >= ncols) z[i] = -INFINITY;
+                }
+                float gm = z[0];
+#pragma unroll
+                for (int i = 1; i < 32; ++i) gm = fmaxf(gm, z[i]);
+                if (gm > best) {                        // first arg-max (numpy tie rule)
+                    best = gm;
+#pragma unroll
+                    for (int i = 31; i >= 0; --i) if (z[i] == gm) am = n0 + c0 + i;
+                }
+                const int gcol = n0 + c0;
+                if (gcol + 32 <= a.valid_cols) mv = fmaxf(mv, gm);
+                else if (gcol < a.valid_cols) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (gcol + i < a.valid_cols) mv = fmaxf(mv, z[i]);
+                }
+                if (gm > m) { s *= fast_exp2((m - gm) * kLog2e); m = gm; }
+                const float mb = m * kLog2e;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s += fast_exp2(fmaf(z[i], kLog2e, -mb));
+                if (rm.mode == kRowUniform) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sumz += (c0 + i < ncols) ? z[i] : 0.f;
+                }
+                if (y_local >= c0 && y_local < c0 + 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (i == y_local - c0) zy = z[i];
+                }
+            }
+            // ---- combine with the peer CTA's half of the classes ----
+            if (CL > 1) {
+                const uint32_t par = it & 1;
+                float* mine = sXch + (par * BM + r_in_tile) * 8;
+                const uint32_t peer = rank ^ 1u;
+                const uint32_t raddr = map_to_peer(smem_u32(mine), peer);
+                st_peer_f32(raddr + 0, m); st_peer_f32(raddr + 4, s); st_peer_f32(raddr + 8, best);
+                st_peer_f32(raddr + 12, __int_as_float(am)); st_peer_f32(raddr + 16, mv);
+                st_peer_f32(raddr + 20, sumz); st_peer_f32(raddr + 24, zy);
+                mbar_arrive_peer(map_to_peer(smem_u32(&x_bar[par]), peer));
+                mbar_wait_cluster(&x_bar[par], (it >> 1) & 1);
+                const float pm = mine[0], ps = mine[1], pbest = mine[2];
+                const int pam = __float_as_int(mine[3]);
+                const float pmv = mine[4], psumz = mine[5], pzy = mine[6];
+                const float mg = fmaxf(m, pm);
+                s = s * fast_exp2((m - mg) * kLog2e) + ps * fast_exp2((pm - mg) * kLog2e);
+                m = mg;
+                if (pbest > best || (pbest == best && pam < am)) { best = pbest; am = pam; }
+                mv = fmaxf(mv, pmv); sumz += psumz; zy += pzy;
+            }
+            const float lse = m + fast_log2(s) * kLn2;
+            const bool is_col = (y >= 0 && y < a.C);
+            if (rank == 0 && row_ok) {
+                float rowloss = 0.f;
+                if (rm.mode == kRowOneHot) rowloss = rm.omega * (lse - zy);
+                else if (rm.mode == kRowUniform) rowloss = a.t_uniform * ((float)a.C * lse - sumz);
+                else if (rm.mode == kRowBad) rowloss = __int_as_float(0x7fc00000);
+                loss_acc += (double)rowloss;
+                if (a.row_ptgt) a.row_ptgt[row] = is_col ? fast_exp2((zy - lse) * kLog2e) : 0.f;
+                if (a.row_pmax) a.row_pmax[row] = fast_exp2((mv - lse) * kLog2e);
+                if (a.row_pmax_all) a.row_pmax_all[row] = fast_exp2((best - lse) * kLog2e);
+                if (a.row_pred) a.row_pred[row] = am;
+            }
+            // ---- sweep B: un-scaled grad-logits  dz = (S p - T) / den  -> bf16 -> TMA store ----
+            if (a.write_dz) {
+                const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
+                const float coef = live ? inv_den * rm.omega / s : 0.f;
+                const float t_all = (rm.mode == kRowUniform) ? inv_den * a.t_uniform : 0.f;
+                const float t_hot = (rm.mode == kRowOneHot) ? inv_den * rm.omega : 0.f;
+                const float mb = m * kLog2e;
+                for (int c0 = 0; c0 < ncols; c0 += 64) {
+                    uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
+                    if (lane == 0) tma_store_wait_read<1>();       // the buffer's previous store has left smem
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        if (c0 + h * 32 < ncols16) { tmem_ld32(t_row + c0 + h * 32, v); tmem_ld_wait(); }
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0xff800000u;   // -inf -> exp = 0
+                        }
+                        float g[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float z = __uint_as_float(v[i]);
+                            if (HAS_BIAS) z += sBias[c0 + h * 32 + i];
+                            g[i] = fmaf(coef, fast_exp2(fmaf(z, kLog2e, -mb)), -t_all);
+                        }
+#pragma unroll
+                        for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
+                    }
+                    if (y_local >= c0 && y_local < c0 + 64) {      // the label column: subtract the one-hot part
+                        const float gy = fmaf(coef, fast_exp2((zy - m) * kLog2e), -t_all) - t_hot;
+                        const int cc = y_local - c0;
+                        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sbuf + lane * 128 + (((cc >> 3) ^ (lane & 7)) << 4)) + (cc & 7);
+                        *p = __float2bfloat16_rn(gy);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_dz, sbuf, n0 + c0, tile * BM + q * 32);
+                        tma_store_commit();
+                    }
+                    ++n_stores;
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+        if (lane == 0) tma_store_wait<0>();
+        // ---- deterministic loss reduction: warps in order, CTAs in order ----
+        __shared__ double s_loss[4];
+        double wl = warp_sum(loss_acc);
+        if (lane == 0) s_loss[q] = wl;
+        epi_bar_sync();
+        if (warp == kEpiWarp0 && lane == 0) {
+            // quadrant order 0..3 regardless of which warp owns it
+            a.partials[blockIdx.x] = ((s_loss[0] + s_loss[1]) + s_loss[2]) + s_loss[3];
+            __threadfence();
+            const unsigned t = atomicAdd(a.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                __threadfence();
+                double tot = 0.0;
+                for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(&a.partials[b]);
+                a.loss_num[0] = tot;
+                a.loss[0] = (float)(tot / a.den[0]);
+                *a.ticket = 0u;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, Cfg::kTmemCols);
+}
+
+// =================================================================================================
+// dX = g * dZ W : A = dZ tile (K-major over classes), B = W tile viewed MN-major (N = feature index)
+// =================================================================================================
+constexpr int kDxBN = 256;
+constexpr int kDxStages = 4;
+constexpr int kDxStageBytes = kABytes + 4 * kBoxBytes;          // 48 KB
+constexpr int kDxOffStage = kDxStages * kDxStageBytes;
+constexpr int kDxOffBars = kDxOffStage + 4 * 2 * kStageWarpBytes;
+constexpr int kDxSmemBytes = kDxOffBars + (2 * kDxStages + 4) * 8 + 16 + 1024;
+static_assert(kDxSmemBytes <= 232448, "dx kernel shared memory");
+
+__global__ void __launch_bounds__(kThreads, 1)
+head_dx_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_w,
+               const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, const float* __restrict__ gscale) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sStage = smem + kDxOffStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDxOffBars);
+    uint64_t* full = bars; uint64_t* empty = full + kDxStages;
+    uint64_t* t_full = empty + kDxStages; uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        fence_barrier_init();
+        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dx);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const int m_tiles = (B + BM - 1) / BM, n_tiles = (K + kDxBN - 1) / kDxBN;
+    const int total = m_tiles * n_tiles;
+    const int n_kb = (C + BK - 1) / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int mt = tile / n_tiles, nt = tile % n_tiles;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], kDxStageBytes);
+                    uint8_t* st = smem + s * kDxStageBytes;
+                    tma_load_2d(st, &tm_dz, &full[s], kb * BK, mt * BM);                        // 64 classes x 128 rows
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)                                                  // 64 features x 64 classes
+                        tma_load_2d(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + j * 64, kb * BK);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BM, kDxBN, false, true);
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+                const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+                mbar_wait(&t_empty[buf], tph ^ 1);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + s * kDxStageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+                    const int rem = C - kb * BK;
+                    const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16(tbase + buf * kDxBN, make_desc_kmajor(a_addr + k * 32),
+                                  make_desc_mnmajor(b_addr + k * 2048, kBoxBytes), idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&t_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
+        const float gs = gscale ? gscale[0] : 1.f;
+        uint32_t tc = 0, n_stores = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+            mbar_wait(&t_full[buf], tph);
+            tc_fence_after_sync();
+            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kDxBN; c0 += 64) {
+                uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0 + h * 32, v);
+                    tmem_ld_wait();
+                    float g[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[i]);
+#pragma unroll
+                    for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_dx, sbuf, nt * kDxBN + c0, mt * BM + q * 32);
+                    tma_store_commit();
+                }
+                ++n_stores;
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// =================================================================================================
+// dW partials = dZ^T X over a slice of the batch: both operands MN-major views of row-major tiles
+// =================================================================================================
+constexpr int kDwBN = 256;
+constexpr int kDwStages = 4;
+constexpr int kDwStageBytes = 2 * kBoxBytes + 4 * kBoxBytes;    // 48 KB: dZ 2 boxes + X 4 boxes, 64 rows each
+constexpr int kDwOffBars = kDwStages * kDwStageBytes;
+constexpr int kDwSmemBytes = kDwOffBars + (2 * kDwStages + 1) * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
+               int B, int K, int C, int splits, float* __restrict__ partials) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwOffBars);
+    uint64_t* full = bars; uint64_t* empty = full + kDwStages; uint64_t* t_full = empty + kDwStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDwStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(t_full, 1);
+        fence_barrier_init();
+        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_x);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const int n_tiles = (K + kDwBN - 1) / kDwBN;
+    const int unit = blockIdx.x;
+    const int sp = unit % splits, tile = unit / splits;
+    const int mt = tile / n_tiles, nt = tile % n_tiles;
+    const int kb_total = (B + BK - 1) / BK;
+    const int kb0 = (int)((int64_t)kb_total * sp / splits), kb1 = (int)((int64_t)kb_total * (sp + 1) / splits);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], kDwStageBytes);
+                uint8_t* st = smem + s * kDwStageBytes;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tma_load_2d(st + j * kBoxBytes, &tm_dz, &full[s], mt * BM + j * 64, kb * BK);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tma_load_2d(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + j * 64, kb * BK);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BM, kDwBN, true, true);
+            uint32_t it = 0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after_sync();
+                const uint32_t a_addr = smem_u32(smem + s * kDwStageBytes);
+                const uint32_t b_addr = a_addr + 2 * kBoxBytes;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(tbase, make_desc_mnmajor(a_addr + k * 2048, kBoxBytes),
+                              make_desc_mnmajor(b_addr + k * 2048, kBoxBytes), idesc, (it | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(t_full);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int cls = mt * BM + q * 32 + lane;
+        mbar_wait(t_full, 0);
+        tc_fence_after_sync();
+        float* dst = partials + ((size_t)sp * C + (size_t)(cls < C ? cls : 0)) * K + (size_t)nt * kDwBN;
+        const uint32_t t_row = tmem_addr(tbase, q * 32, 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kDwBN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_row + c0, v);
+            tmem_ld_wait();
+            if (cls < C) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (nt * kDwBN + c0 + i < K) {
+                        float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                               __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                        *reinterpret_cast<float4*>(dst + c0 + i) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, 256);
+}
+
+// dW = g * sum_s partials[s]  (fixed order => deterministic)
+__global__ void __launch_bounds__(256)
+dw_reduce_kernel(const float4* __restrict__ partials, int splits, size_t n4, const float* __restrict__ gscale,
+                 float4* __restrict__ dw) {
+    const float gs = gscale ? gscale[0] : 1.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = partials[i];
+        for (int s = 1; s < splits; ++s) {
+            const float4 p = partials[(size_t)s * n4 + i];
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        acc.x *= gs; acc.y *= gs; acc.z *= gs; acc.w *= gs;
+        dw[i] = acc;
+    }
+}
+
+// db = g * column sums of dZ (bf16 [B, lddz]); one block per 64 columns, fixed summation order
+__global__ void __launch_bounds__(256)
+db_kernel(const __nv_bfloat16* __restrict__ dz, int64_t lddz, int B, int C, const float* __restrict__ gscale,
+          float* __restrict__ db) {
+    __shared__ float sh[4][64];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int part = threadIdx.x >> 6;
+    float acc = 0.f;
+    if (c < C)
+        for (int r = part; r < B; r += 4) acc += __bfloat162float(dz[(int64_t)r * lddz + c]);
+    sh[part][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < C) {
+        const float gs = gscale ? gscale[0] : 1.f;
+        db[c] = gs * (((sh[0][threadIdx.x] + sh[1][threadIdx.x]) + sh[2][threadIdx.x]) + sh[3][threadIdx.x]);
+    }
+}
+
+// ---- host --------------------------------------------------------------------------------------
+static int dw_splits(int B, int K, int C) {
+    const int mt = (C + BM - 1) / BM, nt = (K + kDwBN - 1) / kDwBN;
+    const int kb_total = (B + BK - 1) / BK;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    int s = sms / (mt * nt);
+    if (s < 1) s = 1;
+    if (s > 16) s = 16;
+    if (s > kb_total) s = kb_total < 1 ? 1 : kb_total;
+    return s;
+}
+
+template <typename KernelT>
+static int set_smem(KernelT kernel, int bytes) {
+    OSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return OSB_OK;
+}
+
+template <int BN, int NCHUNK, int CL, int NBUF, int SA, int SB>
+static int launch_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
+                      cudaStream_t st) {
+    using Cfg = FwdCfg<BN, NCHUNK, CL, NBUF, SA, SB>;
+    const int n_tiles = (a.B + BM - 1) / BM;
+    int sms = sm_count();
+    int clusters = sms / CL;
+    if (clusters > n_tiles) clusters = n_tiles;
+    if (clusters < 1) clusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (a.bias) {
+        auto k = head_fwd_kernel<BN, NCHUNK, CL, NBUF, SA, SB, true>;
+        int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a));
+    } else {
+        auto k = head_fwd_kernel<BN, NCHUNK, CL, NBUF, SA, SB, false>;
+        int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a));
+    }
+    return OSB_OK;
+}
+
+static int fwd_box_rows(int C) { return C <= 128 ? 128 : 256; }
+
+}  // namespace head
+}  // namespace osb
+
+using namespace osb;
+using namespace osb::head;
+
+static inline int64_t round_up8(int64_t v) { return (v + 7) / 8 * 8; }
+
+extern "C" size_t osb_head_workspace_bytes(int64_t B, int K, int C) {
+    if (B < 0 || K <= 0 || C <= 0) return 0;
+    const int s = dw_splits((int)B, K, C);
+    return kHeadTicketBytes + sizeof(double) * kMaxPartials + align_up((size_t)s * C * K * sizeof(float), 256) + 256;
+}
+
+#define OSB_TMAP(call, what)                                                              \
+    do {                                                                                  \
+        int rc__ = (call);                                                                \
+        if (rc__ != 0) {                                                                  \
+            osb::set_error("cuTensorMapEncodeTiled failed for %s (code %d)", what, rc__); \
+            return OSB_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+static int check_head_shapes(const char* fn, int64_t B, int K, int C, int64_t ldx) {
+    OSB_REQUIRE(B >= 1 && B < (1LL << 30), OSB_ERR_ARG, "%s: bad batch B=%lld", fn, (long long)B);
+    OSB_REQUIRE(K >= 64 && K % 64 == 0, OSB_ERR_SHAPE, "%s: in_features K=%d must be a positive multiple of 64", fn, K);
+    OSB_REQUIRE(C >= 2 && C <= 1024, OSB_ERR_SHAPE, "%s: head width C=%d outside [2,1024]", fn, C);
+    OSB_REQUIRE(ldx >= K && ldx % 8 == 0, OSB_ERR_ARG, "%s: ldx=%lld must be >= K and a multiple of 8", fn, (long long)ldx);
+    return OSB_OK;
+}
+
+extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
+                                const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
+                                int64_t ignore_index, const double* den, int valid_cols,
+                                double* loss_num, float* loss,
+                                float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
+                                void* dz, int64_t lddz, void* ws, size_t ws_bytes, void* stream) {
+    OSB_ENTRY_GUARD();
+    OSB_REQUIRE(x && w && y && den && loss_num && loss && ws, OSB_ERR_ARG, "osb_head_forward: null pointer");
+    int rc = check_head_shapes("osb_head_forward", B, K, C, ldx);
+    if (rc) return rc;
+    OSB_REQUIRE(variant >= OSB_ENTROPIC && variant <= OSB_GARBAGE, OSB_ERR_ARG, "osb_head_forward: bad variant %d", variant);
+    OSB_REQUIRE(variant != OSB_GARBAGE || class_w, OSB_ERR_ARG, "osb_head_forward: garbage variant needs class_w");
+    OSB_REQUIRE(valid_cols >= 1 && valid_cols <= C, OSB_ERR_ARG, "osb_head_forward: valid_cols=%d outside [1,%d]", valid_cols, C);
+    OSB_REQUIRE(!dz || (lddz >= C && lddz % 8 == 0), OSB_ERR_ARG, "osb_head_forward: lddz=%lld must be >= C and a multiple of 8", (long long)lddz);
+    OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)dz % 16 == 0), OSB_ERR_ARG,
+                "osb_head_forward: x, w and dz must be 16-byte aligned");
+    OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "osb_head_forward: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tx, tw, tdz;
+    OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, BM), "x");
+    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, fwd_box_rows(C)), "w");
+    // without a dz buffer the store map is never used; point it at x so the encode stays valid
+    if (dz) OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 32), "dz");
+    else tdz = tx;
+    FwdArgs a;
+    a.bias = bias; a.y = y; a.class_w = class_w; a.B = (int)B; a.K = K; a.C = C; a.variant = variant;
+    a.t_uniform = (float)(unk_weight / (double)C);
+    a.ignore_index = ignore_index; a.den = den; a.valid_cols = valid_cols;
+    a.loss_num = loss_num; a.loss = loss;
+    a.row_ptgt = row_ptgt; a.row_pmax = row_pmax; a.row_pmax_all = row_pmax_all; a.row_pred = row_pred;
+    a.write_dz = dz ? 1 : 0;
+    a.ticket = reinterpret_cast<unsigned int*>(ws);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kHeadTicketBytes);
+    if (C <= 128) return launch_fwd<128, 1, 1, 2, 4, 4>(tx, tw, tdz, a, st);
+    if (C <= 256) return launch_fwd<256, 1, 1, 2, 3, 3>(tx, tw, tdz, a, st);
+    if (C <= 512) return launch_fwd<256, 2, 1, 1, 3, 4>(tx, tw, tdz, a, st);
+    return launch_fwd<256, 2, 2, 1, 3, 4>(tx, tw, tdz, a, st);
+}
+
+extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
+                                 int64_t B, int K, int C, const float* gscale,
+                                 void* dx, int64_t lddx, float* dw, float* db,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    OSB_ENTRY_GUARD();
+    OSB_REQUIRE(dz && x && w && ws, OSB_ERR_ARG, "osb_head_backward: null pointer");
+    int rc = check_head_shapes("osb_head_backward", B, K, C, ldx);
+    if (rc) return rc;
+    OSB_REQUIRE(lddz >= C && lddz % 8 == 0, OSB_ERR_ARG, "osb_head_backward: lddz=%lld must be >= C and a multiple of 8", (long long)lddz);
+    OSB_REQUIRE(!dx || (lddx >= K && lddx % 8 == 0), OSB_ERR_ARG, "osb_head_backward: bad lddx=%lld", (long long)lddx);
+    OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)dz % 16 == 0) &&
+                ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0), OSB_ERR_ARG,
+                "osb_head_backward: x, w, dz, dx and dw must be 16-byte aligned");
+    OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "osb_head_backward: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dx) {
+        CUtensorMap tdz, tw, tdx;
+        OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, BM), "dz (K-major)");
+        OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, 64), "w (MN-major)");
+        OSB_TMAP(make_tmap_bf16(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx");
+        rc = set_smem(head_dx_kernel, kDxSmemBytes);
+        if (rc) return rc;
+        const int total = (int)((B + BM - 1) / BM) * ((K + kDxBN - 1) / kDxBN);
+        int grid = sm_count();
+        if (grid > total) grid = total;
+        head_dx_kernel<<<grid, kThreads, kDxSmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
+        OSB_LAUNCH_CHECK();
+    }
+    if (dw) {
+        CUtensorMap tdz, tx;
+        OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 64), "dz (MN-major)");
+        OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
+        rc = set_smem(head_dw_kernel, kDwSmemBytes);
+        if (rc) return rc;
+        const int splits = dw_splits((int)B, K, C);
+        const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
+        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kHeadTicketBytes + sizeof(double) * kMaxPartials);
+        partials = reinterpret_cast<float*>(align_up((size_t)partials, 256));
+        head_dw_kernel<<<units, kThreads, kDwSmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
+        OSB_LAUNCH_CHECK();
+        const size_t n4 = (size_t)C * K / 4;
+        int rgrid = (int)((n4 + 255) / 256);
+        const int cap = sm_count() * 8;
+        if (rgrid > cap) rgrid = cap;
+        dw_reduce_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, n4, gscale,
+                                                reinterpret_cast<float4*>(dw));
+        OSB_LAUNCH_CHECK();
+    }
+    if (db) {
+        db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, gscale, db);
+        OSB_LAUNCH_CHECK();
+    }
+    return OSB_OK;
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "../openset_imagenet_b200/csrc/tc05.cuh"
 
 using namespace osb;
@@ -14,7 +15,7 @@ using namespace osb::tc;
 constexpr int M = 128, N = 256, KD = 128, KB = 64;       // two k-blocks of 64
 constexpr int A_STAGE = M * KB * 2, B_STAGE = N * KB * 2;
 
-struct Variant { int a_mn, b_mn; uint32_t lbo_a, sbo_a, lbo_b, sbo_b; };
+struct Variant { int a_mn, b_mn; uint32_t lbo_a, sbo_a, lbo_b, sbo_b; int a_fp16; };
 
 __device__ int g_timeout;
 
@@ -51,7 +52,8 @@ probe_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUt
             if (!v.b_mn) tma_load_2d(sb + s * B_STAGE, &tb, &full[s], s * KB, 0);                // box 64(K) x 256 rows
             else for (int j = 0; j < N / 64; ++j) tma_load_2d(sb + s * B_STAGE + j * 8192, &tb, &full[s], j * 64, s * KB);
         }
-        const uint32_t idesc = make_idesc_bf16(M, N, v.a_mn, v.b_mn);
+        uint32_t idesc = make_idesc_bf16(M, N, v.a_mn, v.b_mn);
+        if (v.a_fp16) idesc &= ~(7u << 7);          // A format field = F16 (0), B stays BF16
         bool ok = true;
         for (int s = 0; s < 2 && ok; ++s) {
             ok = wait_bounded(&full[s], 0);
@@ -96,9 +98,13 @@ int main() {
             ref[m * N + n] = s;
         }
     std::vector<__nv_bfloat16> Ak(M * KD), At(KD * M), Bk(N * KD), Bt(KD * N);
-    for (int m = 0; m < M; ++m) for (int k = 0; k < KD; ++k) { Ak[m * KD + k] = __float2bfloat16(A[m * KD + k]); At[k * M + m] = Ak[m * KD + k]; }
+    std::vector<__half> Akh(M * KD), Ath(KD * M);
+    for (int m = 0; m < M; ++m) for (int k = 0; k < KD; ++k) { Ak[m * KD + k] = __float2bfloat16(A[m * KD + k]); At[k * M + m] = Ak[m * KD + k]; Akh[m * KD + k] = __float2half(A[m * KD + k]); Ath[k * M + m] = Akh[m * KD + k]; }
     for (int n = 0; n < N; ++n) for (int k = 0; k < KD; ++k) { Bk[n * KD + k] = __float2bfloat16(B[n * KD + k]); Bt[k * N + n] = Bk[n * KD + k]; }
-    __nv_bfloat16 *dAk, *dAt, *dBk, *dBt; float* dout;
+    __nv_bfloat16 *dAk, *dAt, *dBk, *dBt; float* dout; __half *dAkh, *dAth;
+    CK(cudaMalloc(&dAkh, Akh.size() * 2)); CK(cudaMalloc(&dAth, Ath.size() * 2));
+    CK(cudaMemcpy(dAkh, Akh.data(), Akh.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dAth, Ath.data(), Ath.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dAk, Ak.size() * 2)); CK(cudaMalloc(&dAt, At.size() * 2));
     CK(cudaMalloc(&dBk, Bk.size() * 2)); CK(cudaMalloc(&dBt, Bt.size() * 2));
     CK(cudaMalloc(&dout, M * N * 4));
@@ -106,7 +112,8 @@ int main() {
     CK(cudaMemcpy(dAt, At.data(), At.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dBk, Bk.data(), Bk.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dBt, Bt.data(), Bt.size() * 2, cudaMemcpyHostToDevice));
-    CUtensorMap tAk, tAt, tBk, tBt;
+    CUtensorMap tAk, tAt, tBk, tBt, tAkh, tAth;
+    if (make_tmap_bf16(&tAkh, dAkh, M, KD, KD, 128) || make_tmap_bf16(&tAth, dAth, KD, M, M, 64)) { printf("tensor map encode failed\n"); return 3; }
     if (make_tmap_bf16(&tAk, dAk, M, KD, KD, 128) || make_tmap_bf16(&tAt, dAt, KD, M, M, 64) ||
         make_tmap_bf16(&tBk, dBk, N, KD, KD, 256) || make_tmap_bf16(&tBt, dBt, KD, N, N, 64)) {
         printf("tensor map encode failed\n");
@@ -116,13 +123,15 @@ int main() {
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     struct Named { const char* name; Variant v; };
     Named variants[] = {
-        {"A=K  B=K   (lbo 0, sbo 1024)", {0, 0, 0, 1024, 0, 1024}},
-        {"A=MN B=K   (lbo 8192, sbo 1024)", {1, 0, 8192, 1024, 0, 1024}},
-        {"A=K  B=MN  (lbo 8192, sbo 1024)", {0, 1, 0, 1024, 8192, 1024}},
-        {"A=MN B=MN  (lbo 8192, sbo 1024)", {1, 1, 8192, 1024, 8192, 1024}},
-        {"A=MN B=K   SWAPPED (lbo 1024, sbo 8192)", {1, 0, 1024, 8192, 0, 1024}},
-        {"A=K  B=MN  SWAPPED (lbo 1024, sbo 8192)", {0, 1, 0, 1024, 1024, 8192}},
-        {"A=K  B=K   (lbo 16, sbo 1024)", {0, 0, 16, 1024, 16, 1024}},
+        {"A=K  B=K   (lbo 0, sbo 1024)", {0, 0, 0, 1024, 0, 1024, 0}},
+        {"A=MN B=K   (lbo 8192, sbo 1024)", {1, 0, 8192, 1024, 0, 1024, 0}},
+        {"A=K  B=MN  (lbo 8192, sbo 1024)", {0, 1, 0, 1024, 8192, 1024, 0}},
+        {"A=MN B=MN  (lbo 8192, sbo 1024)", {1, 1, 8192, 1024, 8192, 1024, 0}},
+        {"A=MN B=K   SWAPPED (lbo 1024, sbo 8192)", {1, 0, 1024, 8192, 0, 1024, 0}},
+        {"A=K  B=MN  SWAPPED (lbo 1024, sbo 8192)", {0, 1, 0, 1024, 1024, 8192, 0}},
+        {"A=K  B=K   (lbo 16, sbo 1024)", {0, 0, 16, 1024, 16, 1024, 0}},
+        {"A=K(fp16)  B=K(bf16)  mixed formats", {0, 0, 0, 1024, 0, 1024, 1}},
+        {"A=MN(fp16) B=MN(bf16) mixed formats", {1, 1, 8192, 1024, 8192, 1024, 1}},
     };
     std::vector<float> got(M * N);
     int fails = 0;
@@ -130,7 +139,7 @@ int main() {
         CK(cudaMemset(dout, 0xff, M * N * 4));
         int zero = 0;
         CK(cudaMemcpyToSymbol(g_timeout, &zero, sizeof(int)));
-        probe_kernel<<<1, 128, smem_bytes>>>(nv.v.a_mn ? tAt : tAk, nv.v.b_mn ? tBt : tBk, nv.v, dout);
+        probe_kernel<<<1, 128, smem_bytes>>>(nv.v.a_fp16 ? (nv.v.a_mn ? tAth : tAkh) : (nv.v.a_mn ? tAt : tAk), nv.v.b_mn ? tBt : tBk, nv.v, dout);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("%-44s CUDA ERROR %s\n", nv.name, cudaGetErrorName(e)); return 4; }
         int to = 0;
