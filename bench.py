@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native open-set head + OSCR path (contract: see the task statement / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload head|bg|oscr]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Default workload ("head") = BASELINE.json's large-head configuration, the largest one that fits one GPU and
+the one its tensor-core target is quoted on: entropic open-set loss over a 2048 -> 1000 head on 16384
+bf16 feature rows PER GPU (1/3 negatives), forward + backward (loss, confidence statistics, dX, dW).
+A "step" is one such pass; with N GPUs the batch is sharded (weak scaling: 16384 rows per GPU) and the fp32
+dW (+loss) buffer is all-reduced with NCCL every step.  The same JSON line carries an "oscr" object: OSCR
+over 1M x 116 synthetic scores (BASELINE.json's second headline metric), sharded by rows for N > 1.
+
+One JSON line is printed by rank 0.  `value` is device throughput with inputs resident in HBM; `e2e` is
+the same step driven through the C ABI from pinned HOST buffers (H2D of features+labels, D2H of loss, dX
+and dW inside the timed region).  `--impl reference` times the CPU port of the reference's own path
+(oracle/ref_port.py) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+HEAD = dict(B=16384, K=2048, C=1000, variant="entropic", neg_frac=1.0 / 3.0)
+BG = dict(B=1024, K=2048, C=152, variant="garbage", neg_frac=1.0 / 3.0)
+OSCR = dict(N=1_000_000, C=116)
+METRIC = "EOS head fwd+bwd samples/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4, "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_head_inputs(cfg, dev, nbuf, seed):
+    from oracle import oracle as O
+    g = torch.Generator(device=dev).manual_seed(seed)
+    xs = [torch.randn(cfg["B"], cfg["K"], device=dev, generator=g).bfloat16() for _ in range(nbuf)]
+    if cfg["variant"] == "garbage":
+        ys_np = [O.make_labels(cfg["B"], cfg["C"] - 1, cfg["neg_frac"], seed=seed + i, neg_label=cfg["C"] - 1) for i in range(nbuf)]
+        cw = torch.tensor(O.class_weights_from_labels(np.concatenate(ys_np + [np.arange(cfg["C"])]), cfg["C"]), device=dev)
+    else:
+        ys_np = [O.make_labels(cfg["B"], cfg["C"], cfg["neg_frac"], seed=seed + i) for i in range(nbuf)]
+        cw = None
+    ys = [torch.tensor(y, device=dev) for y in ys_np]
+    w = (torch.randn(cfg["C"], cfg["K"], device=dev, generator=g) * (1.0 / cfg["K"] ** 0.5)).bfloat16()
+    return xs, ys, ys_np, w, cw
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_head(args, cfg, rank, world, dev, peaks):
+    import torch.distributed as dist
+    from openset_imagenet_b200.functional import HeadPlan
+
+    B, K, C = cfg["B"], cfg["K"], cfg["C"]
+    nbuf = 3                                        # 3 x 64 MB of features + 64 MB dX + 32 MB dZ: far larger than the 126 MB L2
+    xs, ys, ys_np, w, cw = make_head_inputs(cfg, dev, nbuf, seed=1234 + rank)
+    plan = HeadPlan(B, K, C, cfg["variant"], class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None,
+                    device=dev)
+    den_hook = None
+    flat = torch.empty(C * K + 2, dtype=torch.float32, device=dev)
+    if world > 1:
+        def den_hook(den):                          # global mean: the denominator is summed over the shards
+            dist.all_reduce(den, op=dist.ReduceOp.SUM)
+
+    def step(i, ev=None):
+        x, y = xs[i % nbuf], ys[i % nbuf]
+        plan.label_stats(y, den_hook)
+        if ev: ev[0].record()
+        plan.forward(x, w, y)
+        if ev: ev[1].record()
+        plan.backward_dw(x, w)
+        if ev: ev[2].record()
+        if world > 1:                               # dW first so its all-reduce can overlap the dX GEMM
+            flat[:C * K].copy_(plan.dw.view(-1))
+            flat[C * K] = plan.loss[0]
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+        plan.backward_dx(x, w)
+        if ev: ev[3].record()
+        if world > 1:
+            work.wait()
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clk:
+        t0.record()
+        for i in range(args.steps):
+            step(i, evs[i])
+        t1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    k_fwd = statistics.mean(e[0].elapsed_time(e[1]) for e in evs) * 1e3
+    k_dw = statistics.mean(e[1].elapsed_time(e[2]) for e in evs) * 1e3
+    k_dx = statistics.mean(e[2].elapsed_time(e[3]) for e in evs) * 1e3
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss_val = float(plan.loss.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    gemm_flops = 2.0 * B * K * C
+    kernels = {"head_fwd_kernel": k_fwd, "head_dw_kernel+dw_reduce_kernel": k_dw, "head_dx_kernel": k_dx}
+    dom = max(kernels, key=kernels.get)
+    step_us = ms_per_step * 1e3
+    roof = {
+        "bound": "tensor", "kernel": dom, "unit": "TFLOP/s",
+        "achieved": gemm_flops / kernels[dom] / 1e6, "peak": peaks["tc_sustained"],
+        "peak_kind": f"{peaks['src']} cuBLAS bf16 sustained (kernels timed inside a long step); burst is {peaks['tc_burst']}",
+        "traffic": None,
+        "kernels_us": {k: round(v, 2) for k, v in kernels.items()},
+        "kernels_tflops": {k: round(gemm_flops / v / 1e6, 1) for k, v in kernels.items()},
+        "step": {"flops": 3 * gemm_flops, "us": round(step_us, 2), "achieved": 3 * gemm_flops / step_us / 1e6,
+                 "frac": 3 * gemm_flops / step_us / 1e6 / peaks["tc_sustained"]},
+        "algorithmic_flops_per_sample": 6.0 * K * C,
+    }
+    roof["frac"] = roof["achieved"] / roof["peak"]
+
+    # ---- end to end from pinned host buffers through the C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        hx = [x.cpu().pin_memory() for x in xs[:2]]
+        hy = [y.cpu().pin_memory() for y in ys[:2]]
+        dxh = torch.empty(B, K, dtype=torch.bfloat16).pin_memory()
+        dwh = torch.empty(C, K, dtype=torch.float32).pin_memory()
+        lossh = torch.empty(1, dtype=torch.float32).pin_memory()
+        xd, yd = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+        n_e2e = max(3, min(args.steps, 40))
+
+        def e2e_step(i):
+            xd.copy_(hx[i % 2], non_blocking=True)
+            yd.copy_(hy[i % 2], non_blocking=True)
+            plan.step(xd, w, yd, den_scale_hook=den_hook)
+            lossh.copy_(plan.loss, non_blocking=True)
+            dxh.copy_(plan.dx, non_blocking=True)
+            dwh.copy_(plan.dw, non_blocking=True)
+
+        for i in range(3):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n_e2e):
+            e2e_step(i)
+        b.record()
+        torch.cuda.synchronize()
+        ems = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": world * B * n_e2e / (ems * 1e-3), "unit": "samples/s", "steps": n_e2e,
+               "h2d_bytes_per_step": B * K * 2 + B * 8, "d2h_bytes_per_step": B * K * 2 + C * K * 4 + 4,
+               "ms_per_step": ems / n_e2e}
+    return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clk.summary(), loss=loss_val,
+                launches=plan.launches_per_step * args.steps)
+
+
+def run_oscr(args, rank, world, dev, peaks):
+    """OSCR ms @ 1M scores.  N > 1: rows sharded, known keys all-gathered, counts merged by one all-reduce."""
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from openset_imagenet_b200.util import calculate_oscr_device
+
+    N, C = OSCR["N"], OSCR["C"]
+    gt_np, s_np = O.make_oscr_case(N, C, seed=0)
+    n_loc = N // world
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    s = torch.tensor(s_np[sl], device=dev)
+    gt = torch.tensor(gt_np[sl], device=dev)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+    if world > 1:
+        from openset_imagenet_b200.dist import calculate_oscr_sharded
+
+        def run():
+            return calculate_oscr_sharded(gt, s, -1)
+    else:
+        def run():
+            return calculate_oscr_device(gt, s, -1)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    iters = 15
+    for _ in range(iters):
+        flush.fill_(0)                                   # 464 MB of scores already exceed L2; flush anyway
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = run()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    ms = statistics.median(times)
+    if world == 1:
+        meta = r.meta.tolist()
+        n_thr = max(meta[0] - 1, 0)
+    else:
+        n_thr = max(int(r[5][0].item()) - 1, 0)
+    alg_bytes = 4.0 * N * C + 8.0 * N + 16.0 * n_thr
+    out = {"metric": "OSCR ms @1M scores", "value": ms, "unit": "ms", "higher_is_better": False,
+           "config": {"workload": f"OSCR CCR/FPR over N={N} x C={C} float32 scores, 50% known / 25% -1 / 25% -2, unk_label=-1",
+                      "rows_per_gpu": n_loc, "n_thresholds": n_thr},
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "peak_kind": f"{peaks['src']} copy bandwidth", "algorithmic_bytes": alg_bytes, "traffic": None}}
+    out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
+    if rank == 0 and world == 1 and not args.no_e2e:
+        import openset_imagenet_b200 as osb
+        hs, hg = torch.from_numpy(s_np).pin_memory(), torch.from_numpy(gt_np).pin_memory()
+        osb.calculate_oscr(hg, hs, -1)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ccr, fpr = osb.calculate_oscr(hg, hs, -1)
+        e_ms = (time.perf_counter() - t0) / reps * 1e3
+        out["e2e"] = {"value": e_ms, "unit": "ms", "h2d_bytes_per_step": N * C * 4 + N * 8, "d2h_bytes_per_step": 16 * n_thr + 40}
+        t0 = time.perf_counter()
+        o_ccr, o_fpr = O.calculate_oscr(gt_np, s_np, -1)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        n_q = 8000
+        from oracle import ref_port
+        t0 = time.perf_counter()
+        ref_port.oscr_port_quadratic(gt_np[:n_q], s_np[:n_q], -1)
+        q_ms = (time.perf_counter() - t0) * 1e3
+        out["cpu_baseline"] = {"value": cpu_ms, "unit": "ms", "cores": 1, "kind": "port",
+                               "sample": f"O(N log N) numpy restatement (oracle.calculate_oscr, bit-equal to the reference) on the full N={N}; "
+                                         f"numpy sort is single-threaded",
+                               "reference_quadratic": {"n": n_q, "ms": q_ms, "extrapolated_ms_at_1M": q_ms * (N / n_q) ** 2,
+                                                       "note": "reference's own O(U*N) loop (util.py:113-118) timed at n rows; 1M figure is an N^2 extrapolation"}}
+        out["parity"] = {"bit_exact_vs_oracle": bool(np.array_equal(ccr, o_ccr) and np.array_equal(fpr, o_fpr, equal_nan=True))}
+    return out
+
+
+def head_cpu_baseline(cfg, sample_rows, iters):
+    """The reference path op for op on the host cores (oracle/ref_port.py), on `sample_rows` rows of the workload."""
+    from oracle import oracle as O
+    from oracle import ref_port
+    torch.manual_seed(0)
+    K, C = cfg["K"], cfg["C"]
+    lin = torch.nn.Linear(K, C, bias=False)
+    loss_fn = ref_port.EntropicLossPort(C, 1.0)
+    x = torch.randn(sample_rows, K, requires_grad=True)
+    y = torch.tensor(O.make_labels(sample_rows, C, cfg["neg_frac"], seed=7))
+    ref_port.head_step_port(lin, loss_fn, x, y, 1.0 / C)
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        ref_port.head_step_port(lin, loss_fn, x, y, 1.0 / C)
+        ts.append(time.perf_counter() - t0)
+    return sample_rows / statistics.median(ts), ts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="head", choices=["head", "bg", "oscr"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-oscr", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local = dist_env()
+    cfg = HEAD if args.workload != "bg" else BG
+    workload_name = (f"{cfg['variant']} open-set head fwd+bwd, {cfg['K']}->{cfg['C']} classes, {cfg['B']} bf16 feature rows per GPU, "
+                     f"{cfg['neg_frac']:.2f} negatives (BASELINE.json {'large-head stress config' if cfg is HEAD else 'BG config'})")
+    peaks = load_peaks()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        # bounded sample: size the per-step sample so steps+warmup stay within ~2 minutes
+        v0, ts = head_cpu_baseline(cfg, 256, 1)
+        per_row = ts[0] / 256
+        rows = int(min(cfg["B"], max(64, 90.0 / max(per_row * (args.steps + args.warmup), 1e-9))))
+        rows = 1 << (rows.bit_length() - 1)
+        rows = max(64, min(rows, 4096))
+        value, ts = head_cpu_baseline(cfg, rows, max(1, min(args.steps, 200)))
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": len(ts), "warmup": 1,
+                "ms_per_step": statistics.median(ts) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload_name, "sample_rows_per_step": rows},
+                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{rows} rows per step of the same workload, float32, torch CPU ({torch.get_num_threads()} threads): "
+                                           "nn.Linear -> EntropicOpensetLoss port -> backward -> softmax -> confidence port (oracle/ref_port.py)"},
+                "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA (sm_100a) device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import openset_imagenet_b200  # noqa: F401  (loads libosb.so; raises if missing)
+
+    if args.workload == "oscr":
+        o = run_oscr(args, rank, world, dev, peaks)
+        if rank == 0:
+            o.update({"n_gpus": world, "steps": 15, "warmup": 3, "ms_per_step": o["value"], "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32 keys / int64 counts", "data": "synthetic", "gpu_launches": 15 * 9})
+            print(json.dumps(o))
+    else:
+        r = run_head(args, cfg, rank, world, dev, peaks)
+        oscr = None if args.no_oscr else run_oscr(args, rank, world, dev, peaks)
+        if rank == 0:
+            line = {"metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": workload_name, "global_batch": cfg["B"] * world, "in_features": cfg["K"],
+                               "classes": cfg["C"], "parallelism": f"batch-sharded x{world}, NCCL all-reduce of fp32 dW" if world > 1 else "single GPU",
+                               "l2": "3 rotating 64 MB feature buffers + 64 MB dX + 32 MB dZ per step: working set > 126 MB L2"},
+                    "roofline": r["roofline"], "e2e": r["e2e"], "clocks": r["clocks"], "gpu_launches": r["launches"],
+                    "loss": r["loss"], "peaks": peaks}
+            if world == 1 and not args.no_e2e:
+                torch.set_num_threads(os.cpu_count() or 1)
+                rows = 2048
+                v, ts = head_cpu_baseline(cfg, rows, 5)
+                line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                        "sample": f"{rows} rows of the same workload x 5 steps, float32 torch CPU: nn.Linear -> EntropicOpensetLoss "
+                                                  "port -> backward -> softmax -> confidence port (oracle/ref_port.py)"}
+            if oscr is not None:
+                line["oscr"] = oscr
+            print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

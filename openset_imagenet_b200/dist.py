@@ -1,0 +1,168 @@
+"""Batch-sharded head and sharded OSCR over the GPUs of one box (one process per GPU, NCCL over NVLink).
+
+The reference has no collectives at all (its multi-GPU mode is one independent training job per GPU,
+script/train_all.py:96-118); what is exchanged here follows from the arithmetic:
+
+* head: rows are independent given W, so the batch shards freely.  The loss is a global mean, so the
+  denominator must be global: B_global for the entropic loss (known without communication), one
+  all-reduced double for the softmax / garbage variants.  After backward ONE all-reduce(sum) of the
+  fp32 [dW | db | loss_num] buffer makes every rank hold the full-batch gradient; dX stays local.
+* OSCR: stage A (97 % of the bytes) shards by rows.  Thresholds are the global set of unique known
+  target scores, so the known keys are all-gathered (4 B per known sample); every rank derives the
+  identical threshold list, counts its own shard against it, and ONE all-reduce(sum) of the int64
+  counts merges the shards.  Counts at a fixed threshold are additive across shards, so the result is
+  bit-identical to the single-GPU one.
+
+All of this works on any backend: the CPU tests run the control flow with gloo (world size 2) on fake
+stage results; the GPU path uses nccl.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ------------------------------------------------------------------------------------------------
+# head
+# ------------------------------------------------------------------------------------------------
+class ShardedHead:
+    """Wraps a ``FusedOpenSetHead`` whose batch is sharded across the process group.
+
+    ``loss(features, target)`` returns this shard's contribution ``loss_num_local / den_global``; summing
+    it over ranks gives the reference's full-batch loss, and ``backward()`` then yields
+    ``d(full loss)/d(local features)`` plus this shard's part of dW/db.  ``allreduce_grads()`` sums the
+    packed [dW | db | loss] buffer with one NCCL all-reduce.
+    """
+
+    def __init__(self, head, group=None):
+        self.head = head
+        self.group = group
+        head.den_hook = self._global_den
+        self._flat = None
+
+    def _global_den(self, den: torch.Tensor) -> torch.Tensor:
+        _, ws = world()
+        if ws == 1:
+            return den
+        if self.head.variant_name == "entropic":
+            # every row counts: the global denominator is the global batch size when shards are equal,
+            # otherwise it still needs the sum
+            pass
+        dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
+        return den
+
+    def loss(self, features, target):
+        return self.head.loss(features, target)
+
+    def pack_grads(self, local_loss: torch.Tensor) -> torch.Tensor:
+        parts = [self.head.weight.grad.reshape(-1)]
+        if self.head.bias is not None and self.head.bias.grad is not None:
+            parts.append(self.head.bias.grad.reshape(-1))
+        parts.append(local_loss.detach().reshape(1).float())
+        n = sum(p.numel() for p in parts)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, dtype=torch.float32, device=parts[0].device)
+        torch.cat(parts, out=self._flat)
+        return self._flat
+
+    def allreduce_grads(self, local_loss: torch.Tensor, async_op: bool = False):
+        """One all-reduce for everything the optimiser and the logger need.  Returns (work, unpack)."""
+        flat = self.pack_grads(local_loss)
+        _, ws = world()
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op) if ws > 1 else None
+
+        def unpack():
+            if work is not None and async_op:
+                work.wait()
+            off = 0
+            w = self.head.weight
+            w.grad.copy_(flat[off:off + w.numel()].view_as(w))
+            off += w.numel()
+            if self.head.bias is not None and self.head.bias.grad is not None:
+                b = self.head.bias
+                b.grad.copy_(flat[off:off + b.numel()])
+                off += b.numel()
+            return flat[off]
+
+        return work, unpack
+
+
+# ------------------------------------------------------------------------------------------------
+# OSCR
+# ------------------------------------------------------------------------------------------------
+def merge_counts(ccr_cnt: torch.Tensor, fpr_cnt: torch.Tensor, totals: torch.Tensor, group=None):
+    """The "single small all-reduce" of the sharded OSCR: int64 [ccr counts | fpr counts | totals]."""
+    n = ccr_cnt.numel()
+    buf = torch.cat([ccr_cnt, fpr_cnt, totals])
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf[:n], buf[n:2 * n], buf[2 * n:]
+
+
+def gather_known_keys(keys_known: torch.Tensor, n_local: int, group=None) -> torch.Tensor:
+    """All-gather the fixed-size (absent-key padded) known-key segment of every shard."""
+    _, ws = world()
+    if ws == 1:
+        return keys_known
+    out = torch.empty(ws * n_local, dtype=keys_known.dtype, device=keys_known.device)
+    dist.all_gather_into_tensor(out, keys_known.contiguous(), group=group)
+    return out
+
+
+def calculate_oscr_sharded(gt, scores, unk_label=-1, group=None):
+    """OSCR over a row-sharded evaluation set: every rank passes ITS rows (same shard size on every rank,
+    pad with label -3 rows if needed) and receives the full (ccr, fpr) float64 device tensors plus meta.
+    Bit-identical to ``util.calculate_oscr`` on the concatenated data."""
+    from . import _lib as L
+    from .util import _LABEL_TYPES
+
+    dev = L.require_cuda(scores, gt)
+    rank, ws = world()
+    s = scores if scores.dtype == torch.float32 else scores.float()
+    if s.stride(1) != 1:
+        s = s.contiguous()
+    g = gt if gt.dtype in _LABEL_TYPES else gt.long()
+    g = g.contiguous()
+    n, c = s.shape
+    st = L.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        keys = torch.empty(3 * n, dtype=torch.int32, device=dev)
+        alt = torch.empty(max(3 * n, ws * n), dtype=torch.int32, device=dev)
+        totals = torch.zeros(4, dtype=torch.int64, device=dev)
+        L.call("osb_oscr_rowreduce", L.ptr(s), s.stride(0), L.ptr(g), _LABEL_TYPES[g.dtype], n, c, int(unk_label),
+               L.ptr(keys), L.ptr(totals), st)
+        # local sort of the two count segments; global sort of the gathered threshold segment
+        sws = torch.zeros(L.size("osb_oscr_sort_workspace_bytes", max(n, 1), 2), dtype=torch.uint8, device=dev)
+        L.call("osb_oscr_sort", L.ptr(keys[n:]), L.ptr(alt), n, 2, None, L.ptr(sws), sws.numel(), st)
+        gk = gather_known_keys(keys[:n], n, group).clone()
+        ng = gk.numel()
+        gws = torch.zeros(L.size("osb_oscr_sort_workspace_bytes", max(ng, 1), 1), dtype=torch.uint8, device=dev)
+        galt = torch.empty(ng, dtype=torch.int32, device=dev)
+        L.call("osb_oscr_sort", L.ptr(gk), L.ptr(galt), ng, 1, None, L.ptr(gws), gws.numel(), st)
+        tot_g = totals.clone()
+        if ws > 1:
+            dist.all_reduce(tot_g, op=dist.ReduceOp.SUM, group=group)
+        tau_keys = torch.empty(max(ng, 1), dtype=torch.int32, device=dev)
+        taus = torch.empty(max(ng, 1), dtype=torch.float32, device=dev)
+        n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
+        uws = torch.zeros(L.size("osb_oscr_thresholds_workspace_bytes", max(ng, 1)), dtype=torch.uint8, device=dev)
+        L.call("osb_oscr_thresholds", L.ptr(gk), ng, L.ptr(tot_g[0:1]), L.ptr(tau_keys), L.ptr(taus), L.ptr(n_unique),
+               L.ptr(uws), uws.numel(), st)
+        ccr_cnt = torch.zeros(max(ng, 1), dtype=torch.int64, device=dev)
+        fpr_cnt = torch.zeros(max(ng, 1), dtype=torch.int64, device=dev)
+        L.call("osb_oscr_counts", L.ptr(tau_keys), L.ptr(n_unique), L.ptr(keys[n:]), L.ptr(totals[1:2]),
+               L.ptr(keys[2 * n:]), L.ptr(totals[2:3]), ng, L.ptr(ccr_cnt), L.ptr(fpr_cnt), st)
+        ccr_cnt, fpr_cnt, _ = merge_counts(ccr_cnt, fpr_cnt, torch.zeros(0, dtype=torch.int64, device=dev), group)
+        ccr = torch.empty(max(ng, 1), dtype=torch.float64, device=dev)
+        fpr = torch.empty(max(ng, 1), dtype=torch.float64, device=dev)
+        L.call("osb_oscr_ratios", L.ptr(ccr_cnt), L.ptr(fpr_cnt), L.ptr(n_unique), L.ptr(tot_g[0:1]), L.ptr(tot_g[2:3]),
+               ng, L.ptr(ccr), L.ptr(fpr), st)
+    meta = torch.cat([n_unique, tot_g])
+    return ccr, fpr, ccr_cnt, fpr_cnt, taus, meta

@@ -1,0 +1,92 @@
+"""Allocation-free entry to the fused head: a ``HeadPlan`` owns every buffer one (B, K, C) step needs and
+calls the C ABI directly, so a training loop (or a CUDA graph) replays ``forward`` / ``backward`` with no
+per-step allocations, no autograd bookkeeping and no host synchronisation.
+
+``model.FusedOpenSetHead.loss`` is the autograd-friendly wrapper over the same three entry points.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+_VARIANTS = {"entropic": L.ENTROPIC, "softmax": L.SOFTMAX, "garbage": L.GARBAGE}
+_DEFAULT_IGNORE = {"entropic": -100, "softmax": -1, "garbage": -100}
+
+
+class HeadPlan:
+    """Buffers + launch arguments for linear(K -> C) + open-set loss + backward on a fixed batch size.
+
+    Outputs (device tensors, overwritten by every call):
+      loss [1] f32, loss_num [1] f64, den [1] f64, label_counts [4] i64,
+      p_target / p_max / p_max_all [B] f32, pred [B] i32,
+      dz [B, round_up(C,8)] bf16, dx [B, K] bf16, dw [C, K] f32, db [C] f32 (when bias).
+    """
+
+    def __init__(self, B: int, K: int, C: int, variant: str = "entropic", unk_weight: float = 1.0,
+                 class_weights: torch.Tensor | None = None, ignore_index: int | None = None,
+                 last_valid_class=None, bias: bool = False, device=None):
+        if K % 64 != 0:
+            raise ValueError("HeadPlan needs in_features % 64 == 0 (FusedOpenSetHead pads other widths)")
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.B, self.K, self.C = int(B), int(K), int(C)
+        self.variant = _VARIANTS[variant]
+        self.unk_weight = float(unk_weight)
+        self.ignore_index = int(_DEFAULT_IGNORE[variant] if ignore_index is None else ignore_index)
+        self.valid_cols = len(range(C)[slice(None, last_valid_class)])
+        self.class_w = None if class_weights is None else class_weights.detach().to(self.dev).float().contiguous()
+        d = self.dev
+        self.lddz = (C + 7) // 8 * 8
+        self.ws = torch.zeros(max(L.size("osb_head_workspace_bytes", B, K, C), L.size("osb_loss_workspace_bytes", B)) + 4096,
+                              dtype=torch.uint8, device=d)
+        self.den = torch.empty(1, dtype=torch.float64, device=d)
+        self.label_counts = torch.empty(4, dtype=torch.int64, device=d)
+        self.loss = torch.empty(1, dtype=torch.float32, device=d)
+        self.loss_num = torch.empty(1, dtype=torch.float64, device=d)
+        self.stats = torch.empty(3, B, dtype=torch.float32, device=d)
+        self.p_target, self.p_max, self.p_max_all = self.stats[0], self.stats[1], self.stats[2]
+        self.pred = torch.empty(B, dtype=torch.int32, device=d)
+        self.dz = torch.empty(B, self.lddz, dtype=torch.bfloat16, device=d)
+        self.dx = torch.empty(B, K, dtype=torch.bfloat16, device=d)
+        self.dw = torch.empty(C, K, dtype=torch.float32, device=d)
+        self.db = torch.empty(C, dtype=torch.float32, device=d) if bias else None
+        self.launches_per_step = 5 + (1 if bias else 0)   # label_stats, fwd, dx, dw, dw-reduce (+ db)
+
+    def _check(self, x, w, y):
+        if x.shape != (self.B, self.K) or x.dtype != torch.bfloat16 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous bf16 [B, K] tensor")
+        if w.shape != (self.C, self.K) or w.dtype != torch.bfloat16 or not w.is_contiguous():
+            raise ValueError("w must be a contiguous bf16 [C, K] tensor")
+        if y.shape != (self.B,) or y.dtype != torch.int64:
+            raise ValueError("y must be int64 [B]")
+
+    def label_stats(self, y, den_scale_hook=None):
+        L.call("osb_label_stats", L.ptr(y), L.ptr(self.class_w), self.B, self.C, self.variant, self.ignore_index,
+               L.ptr(self.den), L.ptr(self.label_counts), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+        if den_scale_hook is not None:
+            den_scale_hook(self.den)
+
+    def forward(self, x, w, y, bias=None, write_dz=True):
+        L.call("osb_head_forward", L.ptr(x), self.K, L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(self.class_w),
+               self.B, self.K, self.C, self.variant, self.unk_weight, self.ignore_index, L.ptr(self.den), self.valid_cols,
+               L.ptr(self.loss_num), L.ptr(self.loss), L.ptr(self.p_target), L.ptr(self.p_max), L.ptr(self.p_max_all),
+               L.ptr(self.pred), L.ptr(self.dz) if write_dz else None, self.lddz,
+               L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+
+    def backward_dx(self, x, w, gscale=None):
+        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C,
+               L.ptr(gscale), L.ptr(self.dx), self.K, None, None, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+
+    def backward_dw(self, x, w, gscale=None):
+        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C,
+               L.ptr(gscale), None, self.K, L.ptr(self.dw), L.ptr(self.db), L.ptr(self.ws), self.ws.numel(),
+               L.stream_ptr(self.dev))
+
+    def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False):
+        """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches."""
+        if check:
+            self._check(x, w, y)
+        self.label_stats(y, den_scale_hook)
+        self.forward(x, w, y, bias)
+        self.backward_dx(x, w, gscale)
+        self.backward_dw(x, w, gscale)

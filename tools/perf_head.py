@@ -1,0 +1,89 @@
+"""Per-kernel timing of the fused head and the OSCR stages (developer tool; bench.py is the contract)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from openset_imagenet_b200 import _lib as L
+from openset_imagenet_b200.model import FusedOpenSetHead
+from oracle import oracle as O
+
+dev = torch.device("cuda:0")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def timeit(fn, iters=20, warm=3, flush_l2=True):
+    for _ in range(warm): fn()
+    ts = []
+    for _ in range(iters):
+        if flush_l2: flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+def head_case(B, K, C, variant="entropic"):
+    x = torch.randn(B, K, device=dev).bfloat16()
+    y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=1), device=dev)
+    cw = torch.ones(C, device=dev) if variant == "garbage" else None
+    if variant == "garbage": y = y.clamp(min=0)
+    head = FusedOpenSetHead(K, C, variant=variant, class_weights=cw, device=dev)
+    w = head.weight.detach().bfloat16().contiguous()
+    st = L.stream_ptr(dev)
+    ws = torch.zeros(L.size("osb_head_workspace_bytes", B, K, C) + (1 << 20), dtype=torch.uint8, device=dev)
+    den = torch.full((1,), float(B), dtype=torch.float64, device=dev)
+    counts = torch.empty(4, dtype=torch.int64, device=dev)
+    loss = torch.empty(1, device=dev); num = torch.empty(1, dtype=torch.float64, device=dev)
+    stats = torch.empty(3, B, device=dev); pred = torch.empty(B, dtype=torch.int32, device=dev)
+    lddz = (C + 7) // 8 * 8
+    dz = torch.empty(B, lddz, dtype=torch.bfloat16, device=dev)
+    dx = torch.empty(B, K, dtype=torch.bfloat16, device=dev); dw = torch.empty(C, K, device=dev)
+    vnum = {"entropic": 0, "softmax": 1, "garbage": 2}[variant]
+    def lab(): L.call("osb_label_stats", y.data_ptr(), L.ptr(cw), B, C, vnum, -100, den.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), st)
+    def fwd(): L.call("osb_head_forward", x.data_ptr(), K, w.data_ptr(), None, y.data_ptr(), L.ptr(cw), B, K, C, vnum, 1.0, -100, den.data_ptr(), C,
+                      num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), dz.data_ptr(), lddz, ws.data_ptr(), ws.numel(), st)
+    def fwd_nodz(): L.call("osb_head_forward", x.data_ptr(), K, w.data_ptr(), None, y.data_ptr(), L.ptr(cw), B, K, C, vnum, 1.0, -100, den.data_ptr(), C,
+                      num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), None, lddz, ws.data_ptr(), ws.numel(), st)
+    def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, None, None, ws.data_ptr(), ws.numel(), st)
+    def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, None, K, dw.data_ptr(), None, ws.data_ptr(), ws.numel(), st)
+    def step(): lab(); fwd(); bdx(); bdw()
+    fl = 2.0 * B * K * C
+    print(f"--- head B={B} K={K} C={C} {variant}: GEMM flops each {fl/1e9:.2f} GF")
+    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dw(K3+reduce)", bdw, fl), ("step", step, 3 * fl)]:
+        med, mn = timeit(fn)
+        med2, mn2 = timeit(fn, flush_l2=False)
+        print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | warm med {med2:9.1f} us" + (f" | {f/med/1e6:8.1f} TF/s cold, {f/med2/1e6:8.1f} warm" if f else ""))
+    # cuBLAS reference points for the same three GEMMs
+    xf, wf, dzf = x, w, dz[:, :C].contiguous()
+    for name, fn in [("cublas X@W^T", lambda: xf @ wf.t()), ("cublas dZ@W", lambda: dzf @ wf), ("cublas dZ^T@X", lambda: dzf.t() @ xf)]:
+        med, mn = timeit(fn); print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | {fl/med/1e6:8.1f} TF/s")
+
+def oscr_case(N, C):
+    from openset_imagenet_b200.util import calculate_oscr_device
+    gt, s = O.make_oscr_case(N, C, seed=0)
+    st = torch.tensor(s, device=dev); gtt = torch.tensor(gt, device=dev)
+    stp = L.stream_ptr(dev)
+    ws = torch.zeros(L.size("osb_oscr_workspace_bytes", N) + 4096, dtype=torch.uint8, device=dev)
+    keys = torch.empty(3 * N, dtype=torch.int32, device=dev); alt = torch.empty_like(keys)
+    totals = torch.zeros(4, dtype=torch.int64, device=dev)
+    sws = torch.zeros(L.size("osb_oscr_sort_workspace_bytes", N, 3), dtype=torch.uint8, device=dev)
+    def rr(): L.call("osb_oscr_rowreduce", st.data_ptr(), C, gtt.data_ptr(), 0, N, C, -1, keys.data_ptr(), totals.data_ptr(), stp)
+    def so(): L.call("osb_oscr_sort", keys.data_ptr(), alt.data_ptr(), N, 3, None, sws.data_ptr(), sws.numel(), stp)
+    def full(): calculate_oscr_device(gtt, st, -1)
+    bytes_alg = N * C * 4 + N * 8
+    print(f"--- oscr N={N} C={C}: algorithmic bytes {bytes_alg/1e6:.1f} MB")
+    for name, fn in [("rowreduce", rr), ("sort(3 seg)", so), ("full", full)]:
+        med, mn = timeit(fn)
+        print(f"{name:16s} med {med:9.1f} us min {mn:9.1f} us | {bytes_alg/med/1e3:8.1f} GB/s-equivalent")
+    # confidence
+    from openset_imagenet_b200.metrics import confidence_sums
+    med, mn = timeit(lambda: confidence_sums(st, gtt, 1.0 / C, -1, None))
+    print(f"{'confidence':16s} med {med:9.1f} us min {mn:9.1f} us")
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "head"):
+        head_case(16384, 2048, 1000)
+        head_case(1024, 2048, 152, "garbage")
+        head_case(256, 2048, 116)
+        head_case(64, 2048, 116)
+    if which in ("all", "oscr"):
+        oscr_case(1_000_000, 116)
