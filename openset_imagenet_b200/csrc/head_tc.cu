@@ -32,10 +32,19 @@ constexpr int kBoxBytes = 64 * BK * 2;  // 8 KB: 64 rows x 128 B
 constexpr int kStageWarpBytes = 32 * 128;   // epilogue staging: 32 rows x 128 B per warp
 constexpr int kMaxPartials = 2048;
 constexpr size_t kHeadTicketBytes = 128;
+constexpr int kMaxClusters = 148;
+constexpr size_t kXchFlagBytes = (size_t)kMaxClusters * 2 * 4 * 4 * sizeof(unsigned int);
+constexpr size_t kXchStatBytes = (size_t)kMaxClusters * 2 * 4 * 128 * 6 * sizeof(float);
+// workspace: [ticket][loss partials][exchange flags][exchange statistics][dW partials]
+constexpr size_t kWsOffPartials = kHeadTicketBytes;
+constexpr size_t kWsOffFlags = kWsOffPartials + sizeof(double) * kMaxPartials;
+constexpr size_t kWsOffStats = kWsOffFlags + kXchFlagBytes;
+constexpr size_t kWsOffDw = (kWsOffStats + kXchStatBytes + 255) / 256 * 256;
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // ---- cluster helpers (2-CTA class split) -------------------------------------------------------
@@ -56,8 +65,19 @@ __device__ __forceinline__ uint32_t map_to_peer(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_peer_f32(uint32_t raddr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(raddr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void st_peer_v2(uint32_t raddr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" :: "r"(raddr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_peer(uint32_t raddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(raddr) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -92,43 +112,70 @@ struct FwdArgs {
     float* row_ptgt; float* row_pmax; float* row_pmax_all; int32_t* row_pred;
     int write_dz;
     double* partials; unsigned int* ticket;
+    float* xch_stats;          // [clusters][2][CL][128][6]  per-row statistics exchanged between the CTAs of a cluster
+    unsigned int* xch_flags;   // [clusters][2][CL][4]       release/acquire flags (tile counter), zero between launches
+    long long* trace;      // optional [gridDim.x][64] clock stamps (developer tool, NULL in production)
 };
 
-// BN: rows of one W slot (UMMA N of a full chunk); NCHUNK: chunks per CTA; CL: cluster size (class split);
-// NBUF: TMEM accumulator buffers; SA / SB: ring depths of the X tiles and the W slots.
-template <int BN, int NCHUNK, int CL, int NBUF, int SA, int SB>
+constexpr int kStatFloats = 6;          // m, s, zy, sumz, mv, argmax  (per row, per column slice)
+
+// One CTA owns 128 rows x BN classes of the logits (BN = 128 or 256 TMEM columns, double-buffered so the
+// epilogue of tile t overlaps the MMAs of tile t+1).  Heads wider than BN run as a cluster of CL = ceil(C/BN)
+// CTAs (CL <= 4) that share the rows, split the classes and exchange per-row softmax statistics through DSMEM.
+// EW epilogue warps per TMEM lane quadrant each own a slice of the CTA's columns.
+template <int BN, int CL, int STAGES, int EW>
 struct FwdCfg {
-    static constexpr int kSlotBytes = BN * BK * 2;
-    static constexpr int kBufCols = BN * NCHUNK;                 // accumulator columns per buffer
-    static constexpr int kTmemCols = (kBufCols * NBUF <= 128) ? 128 : (kBufCols * NBUF <= 256 ? 256 : 512);
-    static constexpr int kOffB = SA * kABytes;
-    static constexpr int kOffStage = kOffB + SB * kSlotBytes;
-    static constexpr int kOffXch = kOffStage + 4 * 2 * kStageWarpBytes;      // [2][128][8] floats
-    static constexpr int kOffBias = kOffXch + 2 * BM * 8 * 4;                // [kBufCols] floats
-    static constexpr int kOffBars = kOffBias + kBufCols * 4;
-    static constexpr int kNumBars = 2 * SA + 2 * SB + 2 * NBUF + 2;
+    static constexpr int kThreads = (2 + 4 * EW) * 32;
+    static constexpr int kEpiThreads = 4 * EW * 32;
+    static constexpr int kStageBytes = kABytes + BN * BK * 2;
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kPeers = CL > 1 ? CL - 1 : 1;
+    static constexpr int kOffLx = STAGES * kStageBytes;                            // [2][EW][128][6] floats
+    static constexpr int kOffPx = kOffLx + 2 * EW * BM * kStatFloats * 4;          // [2][CL-1][128][6] floats
+    static constexpr int kOffBias = kOffPx + 2 * kPeers * BM * kStatFloats * 4;    // [BN] floats
+    static constexpr int kOffBars = kOffBias + BN * 4;
+    static constexpr int kNumBars = 2 * STAGES + 4 + 2;
     static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;  // + tmem slot + alignment slack
-    static_assert(kBufCols * NBUF <= 512, "TMEM has 512 columns");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int BN, int NCHUNK, int CL, int NBUF, int SA, int SB, bool HAS_BIAS>
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ float max32(const float (&z)[32]) {
+    float t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = fmaxf(z[i], z[i + 16]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = fmaxf(t[i], t[i + 8]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = fmaxf(t[i], t[i + 4]);
+    return fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+}
+
+// 8 fp32 -> 8 bf16 -> one 16-byte global store
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float* f) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+
+template <int BN, int CL, int STAGES, int EW, bool HAS_BIAS, bool WANT_PRED>
+__global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                const __grid_constant__ CUtensorMap tm_dz, const FwdArgs a) {
-    using Cfg = FwdCfg<BN, NCHUNK, CL, NBUF, SA, SB>;
+                __nv_bfloat16* __restrict__ dz, int64_t lddz, const FwdArgs a) {
+    using Cfg = FwdCfg<BN, CL, STAGES, EW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + Cfg::kOffB;
-    uint8_t* sStage = smem + Cfg::kOffStage;
-    float* sXch = reinterpret_cast<float*>(smem + Cfg::kOffXch);
+    float* sLx = reinterpret_cast<float*>(smem + Cfg::kOffLx);
+    float* sPx = reinterpret_cast<float*>(smem + Cfg::kOffPx);
     float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
-    uint64_t* a_full = bars;              uint64_t* a_empty = a_full + SA;
-    uint64_t* b_full = a_empty + SA;      uint64_t* b_empty = b_full + SB;
-    uint64_t* t_full = b_empty + SB;      uint64_t* t_empty = t_full + NBUF;
-    uint64_t* x_bar = t_empty + NBUF;     // [2] statistics exchange (cluster only)
+    uint64_t* full = bars;                uint64_t* empty = full + STAGES;
+    uint64_t* t_full = empty + STAGES;    uint64_t* t_empty = t_full + 2;
+    uint64_t* x_bar = t_empty + 2;        // [2] statistics exchange with the peer CTAs (cluster only)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,21 +183,19 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int n_tiles = (a.B + BM - 1) / BM;
     const int n_kb = (a.K + BK - 1) / BK;
-    // class range of this CTA
-    const int n0 = (int)rank * (BN * NCHUNK);
-    int ncols = a.C - n0;                                 // real columns owned by this CTA
-    ncols = ncols < 0 ? 0 : (ncols > BN * NCHUNK ? BN * NCHUNK : ncols);
+    const int n0 = (int)rank * BN;                        // class range of this CTA
+    int ncols = a.C - n0;
+    ncols = ncols < 0 ? 0 : (ncols > BN ? BN : ncols);
     const int ncols16 = (ncols + 15) & ~15;               // UMMA N granularity
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        mbar_init(&x_bar[0], BM); mbar_init(&x_bar[1], BM);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * EW); }
+        mbar_init(&x_bar[0], 4 * Cfg::kPeers); mbar_init(&x_bar[1], 4 * Cfg::kPeers);
         fence_barrier_init();
-        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dz);
+        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w);
     }
     if (HAS_BIAS) {
-        for (int i = threadIdx.x; i < BN * NCHUNK; i += kThreads) sBias[i] = (i < ncols) ? a.bias[n0 + i] : 0.f;
+        for (int i = threadIdx.x; i < BN; i += Cfg::kThreads) sBias[i] = (i < ncols) ? a.bias[n0 + i] : 0.f;
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before_sync();
@@ -160,86 +205,83 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
-            uint32_t ia = 0, ib = 0;
+        if (lane == 0 && ncols > 0) {
+            uint32_t it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    const uint32_t s = ia % SA, ph = (ia / SA) & 1; ++ia;
-                    mbar_wait(&a_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&a_full[s], kABytes);
-                    tma_load_2d(sA + s * kABytes, &tm_x, &a_full[s], kb * BK, tile * BM);
-#pragma unroll
-                    for (int j = 0; j < NCHUNK; ++j) {
-                        if (j * BN < ncols16) {
-                            const uint32_t sb = ib % SB, pb = (ib / SB) & 1; ++ib;
-                            mbar_wait(&b_empty[sb], pb ^ 1);
-                            mbar_arrive_expect_tx(&b_full[sb], Cfg::kSlotBytes);
-                            tma_load_2d(sB + sb * Cfg::kSlotBytes, &tm_w, &b_full[sb], kb * BK, n0 + j * BN);
-                        }
-                    }
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                    uint8_t* st = smem + s * Cfg::kStageBytes;
+                    tma_load_2d(st, &tm_x, &full[s], kb * BK, tile * BM);
+                    tma_load_2d(st + kABytes, &tm_w, &full[s], kb * BK, n0);
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------
-        if (lane == 0) {
-            uint32_t ia = 0, ib = 0, it = 0;
-            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
-                const uint32_t buf = it % NBUF, tph = (it / NBUF) & 1;
+        if (lane == 0 && ncols > 0) {
+            const uint32_t idesc = make_idesc_bf16(BM, ncols16, false, false);
+            uint32_t it = 0, tc = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tc) {
+                const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
                 mbar_wait(&t_empty[buf], tph ^ 1);
                 tc_fence_after_sync();
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    const uint32_t s = ia % SA, ph = (ia / SA) & 1; ++ia;
-                    mbar_wait(&a_full[s], ph);
-                    const uint32_t a_addr = smem_u32(sA + s * kABytes);
+                if (a.trace && tc < 4) a.trace[blockIdx.x * 64 + tc * 8 + 0] = gtime();
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    if (a.trace && tc < 4 && kb == 0) a.trace[blockIdx.x * 64 + tc * 8 + 1] = gtime();
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-                    for (int j = 0; j < NCHUNK; ++j) {
-                        if (j * BN < ncols16) {
-                            const int nj = (ncols16 - j * BN) < BN ? (ncols16 - j * BN) : BN;
-                            const uint32_t idesc = make_idesc_bf16(BM, nj, false, false);
-                            const uint32_t sb = ib % SB, pb = (ib / SB) & 1; ++ib;
-                            mbar_wait(&b_full[sb], pb);
-                            tc_fence_after_sync();
-                            const uint32_t b_addr = smem_u32(sB + sb * Cfg::kSlotBytes);
-#pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                umma_bf16(tbase + buf * Cfg::kBufCols + j * BN, make_desc_kmajor(a_addr + k * 32),
-                                          make_desc_kmajor(b_addr + k * 32), idesc, (kb | k) != 0);
-                            umma_commit(&b_empty[sb]);
-                        }
-                    }
-                    umma_commit(&a_empty[s]);
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tbase + buf * BN, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
+                                  idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);
                 }
                 umma_commit(&t_full[buf]);
+                if (a.trace && tc < 4) a.trace[blockIdx.x * 64 + tc * 8 + 2] = gtime();
             }
         }
         __syncwarp();
     } else {
         // ------------------------------ epilogue ----------------------------------
-        const int q = warp & 3;                         // TMEM lane quadrant of this warp
+        // warp (q, h): TMEM lane quadrant q = warp % 4 (hardware rule), column slice h; one thread per row.
+        const int q = warp & 3, h = (warp - kEpiWarp0) >> 2;
         const int r_in_tile = q * 32 + lane;
-        uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
         const float inv_den = (float)(1.0 / a.den[0]);
         const float s_uniform = a.t_uniform * (float)a.C;
+        // this warp's slice of the CTA's columns, in whole 32-column groups
+        const int n32 = (ncols + 31) >> 5, g_per = (n32 + EW - 1) / EW;
+        const int c_lo = h * g_per * 32;
+        int c_hi = (h + 1) * g_per * 32;
+        c_hi = c_hi > ncols ? ncols : c_hi;
+        const bool dz_vec = (lddz % 8 == 0);
         double loss_acc = 0.0;
-        uint32_t it = 0, n_stores = 0;
+        uint32_t it = 0;
         for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
-            const uint32_t buf = it % NBUF, tph = (it / NBUF) & 1;
+            const uint32_t buf = it & 1, tph = (it >> 1) & 1;
             const int row = tile * BM + r_in_tile;
             const bool row_ok = row < a.B;
             const int64_t y = row_ok ? a.y[row] : -1;
             RowMode rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, s_uniform);
             if (!row_ok) { rm.mode = kRowIgnored; rm.omega = 0.f; }
-            const int y_local = (y >= n0 && y < n0 + ncols) ? (int)(y - n0) : -1;
-            mbar_wait(&t_full[buf], tph);
-            tc_fence_after_sync();
-            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * Cfg::kBufCols);
+            const int y_local = (y >= n0 + c_lo && y < n0 + c_hi) ? (int)(y - n0) : -1;   // label column, if in my slice
+            if (ncols > 0) {
+                mbar_wait(&t_full[buf], tph);
+                tc_fence_after_sync();
+            }
+            const bool tr = a.trace && it < 4 && threadIdx.x == kEpiWarp0 * 32;
+            if (tr) a.trace[blockIdx.x * 64 + it * 8 + 3] = gtime();
+            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * BN);
 
-            // ---- sweep A: online softmax statistics over this CTA's columns ----
-            float m = -INFINITY, s = 0.f, sumz = 0.f, zy = 0.f, mv = -INFINITY, best = -INFINITY;
+            // ---- sweep 0: row max (and arg-max / valid-column max) over my slice; no transcendental ----
+            float m = -INFINITY, mv = -INFINITY;
             int am = 0x7fffffff;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(t_row + c0, v);
                 tmem_ld_wait();
@@ -253,56 +295,117 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i) if (c0 + i >= ncols) z[i] = -INFINITY;
                 }
-                float gm = z[0];
+                const float gm = max32(z);
+                if (WANT_PRED) {
+                    if (gm > m) {                       // first arg-max (numpy tie rule): groups ascend, strict '>'
 #pragma unroll
-                for (int i = 1; i < 32; ++i) gm = fmaxf(gm, z[i]);
-                if (gm > best) {                        // first arg-max (numpy tie rule)
-                    best = gm;
-#pragma unroll
-                    for (int i = 31; i >= 0; --i) if (z[i] == gm) am = n0 + c0 + i;
+                        for (int i = 31; i >= 0; --i) if (z[i] == gm) am = n0 + c0 + i;
+                    }
                 }
+                m = fmaxf(m, gm);
                 const int gcol = n0 + c0;
                 if (gcol + 32 <= a.valid_cols) mv = fmaxf(mv, gm);
                 else if (gcol < a.valid_cols) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) if (gcol + i < a.valid_cols) mv = fmaxf(mv, z[i]);
                 }
-                if (gm > m) { s *= fast_exp2((m - gm) * kLog2e); m = gm; }
+            }
+            // ---- sweep 1: e = exp(z - m_slice) written back to TMEM; partial sums with 4-way ILP ----
+            float s = 0.f, sumz = 0.f, zy = 0.f;
+            {
                 const float mb = m * kLog2e;
+                float s4[4] = {0.f, 0.f, 0.f, 0.f}, z4[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0, v);
+                    tmem_ld_wait();
+                    const bool tail = c0 + 32 > ncols;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s += fast_exp2(fmaf(z[i], kLog2e, -mb));
-                if (rm.mode == kRowUniform) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) sumz += (c0 + i < ncols) ? z[i] : 0.f;
+                    for (int i = 0; i < 32; ++i) {
+                        float z = __uint_as_float(v[i]);
+                        if (HAS_BIAS) z += sBias[c0 + i];
+                        if (tail && c0 + i >= ncols) z = -INFINITY;
+                        if (i == y_local - c0) zy = z;
+                        if (rm.mode == kRowUniform) z4[i & 3] += (tail && c0 + i >= ncols) ? 0.f : z;
+                        const float e = fast_exp2(fmaf(z, kLog2e, -mb));
+                        s4[i & 3] += e;
+                        v[i] = __float_as_uint(e);
+                    }
+                    if (a.write_dz) tmem_st32(t_row + c0, v);
                 }
-                if (y_local >= c0 && y_local < c0 + 32) {
+                s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                sumz = (z4[0] + z4[1]) + (z4[2] + z4[3]);
+                if (a.write_dz) tmem_st_wait();
+            }
+            if (tr) a.trace[blockIdx.x * 64 + it * 8 + 4] = gtime();
+            const float m_slice = m;
+            // ---- combine the column slices of this CTA (shared memory), then the CTAs of the cluster (DSMEM) ----
+            {
+                float* lx = sLx + (((it & 1) * EW + h) * BM + r_in_tile) * kStatFloats;
+                lx[0] = m; lx[1] = s; lx[2] = zy; lx[3] = sumz; lx[4] = mv; lx[5] = __int_as_float(am);
+                asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
+                m = -INFINITY; mv = -INFINITY; am = 0x7fffffff;
+                float pm[EW];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (i == y_local - c0) zy = z[i];
+                for (int e = 0; e < EW; ++e) {
+                    const float* o = sLx + (((it & 1) * EW + e) * BM + r_in_tile) * kStatFloats;
+                    pm[e] = o[0];
+                    const int oam = __float_as_int(o[5]);
+                    if (pm[e] > m || (pm[e] == m && oam < am)) am = oam;
+                    m = fmaxf(m, pm[e]);
+                    mv = fmaxf(mv, o[4]);
+                }
+                s = 0.f; zy = 0.f; sumz = 0.f;
+#pragma unroll
+                for (int e = 0; e < EW; ++e) {
+                    const float* o = sLx + (((it & 1) * EW + e) * BM + r_in_tile) * kStatFloats;
+                    s += o[1] * fast_exp2((pm[e] - m) * kLog2e);
+                    zy += o[2]; sumz += o[3];
                 }
             }
-            // ---- combine with the peer CTA's half of the classes ----
             if (CL > 1) {
+                // Through L2, not DSMEM: with the tensor pipe busy on the next tile, remote shared-memory stores
+                // and arrives to a peer SM took ~8 us per tile (measured); a global round trip takes ~1.5 us.
                 const uint32_t par = it & 1;
-                float* mine = sXch + (par * BM + r_in_tile) * 8;
-                const uint32_t peer = rank ^ 1u;
-                const uint32_t raddr = map_to_peer(smem_u32(mine), peer);
-                st_peer_f32(raddr + 0, m); st_peer_f32(raddr + 4, s); st_peer_f32(raddr + 8, best);
-                st_peer_f32(raddr + 12, __int_as_float(am)); st_peer_f32(raddr + 16, mv);
-                st_peer_f32(raddr + 20, sumz); st_peer_f32(raddr + 24, zy);
-                mbar_arrive_peer(map_to_peer(smem_u32(&x_bar[par]), peer));
-                mbar_wait_cluster(&x_bar[par], (it >> 1) & 1);
-                const float pm = mine[0], ps = mine[1], pbest = mine[2];
-                const int pam = __float_as_int(mine[3]);
-                const float pmv = mine[4], psumz = mine[5], pzy = mine[6];
-                const float mg = fmaxf(m, pm);
-                s = s * fast_exp2((m - mg) * kLog2e) + ps * fast_exp2((pm - mg) * kLog2e);
+                float* xs = a.xch_stats + ((size_t)(cluster_id * 2 + par) * CL) * BM * kStatFloats;
+                unsigned int* xf = a.xch_flags + (size_t)(cluster_id * 2 + par) * CL * 4;
+                if (h == 0) {
+                    float2* dst = reinterpret_cast<float2*>(xs + ((size_t)rank * BM + r_in_tile) * kStatFloats);
+                    __stcg(dst + 0, make_float2(m, s)); __stcg(dst + 1, make_float2(zy, sumz));
+                    __stcg(dst + 2, make_float2(mv, __int_as_float(am)));
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) st_release_gpu(xf + rank * 4 + q, it + 1);
+                }
+                if (lane < CL && lane != (int)rank) {
+                    while (ld_acquire_gpu(xf + lane * 4 + q) < it + 1) { }
+                }
+                __syncwarp();
+                float mg = m;
+                float2 pv[Cfg::kPeers][3];
+#pragma unroll
+                for (int d = 1; d < CL; ++d) {
+                    const uint32_t peer = (rank + d) % CL;
+                    const float2* src = reinterpret_cast<const float2*>(xs + ((size_t)peer * BM + r_in_tile) * kStatFloats);
+                    pv[d - 1][0] = __ldcg(src); pv[d - 1][1] = __ldcg(src + 1); pv[d - 1][2] = __ldcg(src + 2);
+                    mg = fmaxf(mg, pv[d - 1][0].x);
+                }
+                s *= fast_exp2((m - mg) * kLog2e);
+                // ties between CTAs resolve to the smaller column index, i.e. scan peers in rank order
+#pragma unroll
+                for (int d = 1; d < CL; ++d) {
+                    const float pm = pv[d - 1][0].x;
+                    const int pam = __float_as_int(pv[d - 1][2].y);
+                    s += pv[d - 1][0].y * fast_exp2((pm - mg) * kLog2e);
+                    if (pm > m || (pm == m && pam < am)) { am = pam; m = pm; }
+                    zy += pv[d - 1][1].x; sumz += pv[d - 1][1].y; mv = fmaxf(mv, pv[d - 1][2].x);
+                }
                 m = mg;
-                if (pbest > best || (pbest == best && pam < am)) { best = pbest; am = pam; }
-                mv = fmaxf(mv, pmv); sumz += psumz; zy += pzy;
             }
+            if (tr) a.trace[blockIdx.x * 64 + it * 8 + 5] = gtime();
             const float lse = m + fast_log2(s) * kLn2;
             const bool is_col = (y >= 0 && y < a.C);
-            if (rank == 0 && row_ok) {
+            if (rank == 0 && h == 0 && row_ok) {
                 float rowloss = 0.f;
                 if (rm.mode == kRowOneHot) rowloss = rm.omega * (lse - zy);
                 else if (rm.mode == kRowUniform) rowloss = a.t_uniform * ((float)a.C * lse - sumz);
@@ -310,65 +413,52 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 loss_acc += (double)rowloss;
                 if (a.row_ptgt) a.row_ptgt[row] = is_col ? fast_exp2((zy - lse) * kLog2e) : 0.f;
                 if (a.row_pmax) a.row_pmax[row] = fast_exp2((mv - lse) * kLog2e);
-                if (a.row_pmax_all) a.row_pmax_all[row] = fast_exp2((best - lse) * kLog2e);
-                if (a.row_pred) a.row_pred[row] = am;
+                if (WANT_PRED) {
+                    if (a.row_pmax_all) a.row_pmax_all[row] = fast_exp2((m - lse) * kLog2e);
+                    if (a.row_pred) a.row_pred[row] = am;
+                }
             }
-            // ---- sweep B: un-scaled grad-logits  dz = (S p - T) / den  -> bf16 -> TMA store ----
+            // ---- sweep 2: un-scaled grad-logits  dz = (S p - T) / den = coef * e - T/den  -> bf16 -> global ----
             if (a.write_dz) {
                 const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
                 const float coef = live ? inv_den * rm.omega / s : 0.f;
+                const float coef_e = coef * fast_exp2((m_slice - m) * kLog2e);   // e was taken relative to the slice max
                 const float t_all = (rm.mode == kRowUniform) ? inv_den * a.t_uniform : 0.f;
                 const float t_hot = (rm.mode == kRowOneHot) ? inv_den * rm.omega : 0.f;
-                const float mb = m * kLog2e;
-                for (int c0 = 0; c0 < ncols; c0 += 64) {
-                    uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
-                    if (lane == 0) tma_store_wait_read<1>();       // the buffer's previous store has left smem
-                    __syncwarp();
+                const float gy = fmaf(coef, fast_exp2((zy - m) * kLog2e), -t_all) - t_hot;   // label column
+                __nv_bfloat16* drow = dz + (int64_t)row * lddz + n0;
+                for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0, v);
+                    tmem_ld_wait();
+                    float g[32];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t v[32];
-                        if (c0 + h * 32 < ncols16) { tmem_ld32(t_row + c0 + h * 32, v); tmem_ld_wait(); }
-                        else {
+                    for (int i = 0; i < 32; ++i) {
+                        g[i] = fmaf(coef_e, __uint_as_float(v[i]), -t_all);
+                        if (i == y_local - c0) g[i] = gy;
+                    }
+                    if (row_ok) {
+                        if (dz_vec && c0 + 32 <= ncols) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = 0xff800000u;   // -inf -> exp = 0
+                            for (int cch = 0; cch < 4; ++cch) store8_bf16(drow + c0 + cch * 8, g + cch * 8);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (c0 + i < ncols) drow[c0 + i] = __float2bfloat16_rn(g[i]);
                         }
-                        float g[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float z = __uint_as_float(v[i]);
-                            if (HAS_BIAS) z += sBias[c0 + h * 32 + i];
-                            g[i] = fmaf(coef, fast_exp2(fmaf(z, kLog2e, -mb)), -t_all);
-                        }
-#pragma unroll
-                        for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
                     }
-                    if (y_local >= c0 && y_local < c0 + 64) {      // the label column: subtract the one-hot part
-                        const float gy = fmaf(coef, fast_exp2((zy - m) * kLog2e), -t_all) - t_hot;
-                        const int cc = y_local - c0;
-                        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sbuf + lane * 128 + (((cc >> 3) ^ (lane & 7)) << 4)) + (cc & 7);
-                        *p = __float2bfloat16_rn(gy);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tm_dz, sbuf, n0 + c0, tile * BM + q * 32);
-                        tma_store_commit();
-                    }
-                    ++n_stores;
                 }
             }
+            if (tr) a.trace[blockIdx.x * 64 + it * 8 + 6] = gtime();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
-        if (lane == 0) tma_store_wait<0>();
-        // ---- deterministic loss reduction: warps in order, CTAs in order ----
+        // ---- deterministic loss reduction: quadrants in order, CTAs in order ----
         __shared__ double s_loss[4];
         double wl = warp_sum(loss_acc);
-        if (lane == 0) s_loss[q] = wl;
-        epi_bar_sync();
+        if (lane == 0 && h == 0) s_loss[q] = wl;
+        asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
         if (warp == kEpiWarp0 && lane == 0) {
-            // quadrant order 0..3 regardless of which warp owns it
             a.partials[blockIdx.x] = ((s_loss[0] + s_loss[1]) + s_loss[2]) + s_loss[3];
             __threadfence();
             const unsigned t = atomicAdd(a.ticket, 1u);
@@ -384,6 +474,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
     tc_fence_before_sync();
     if (CL > 1) cluster_sync_all(); else __syncthreads();
+    if (CL > 1 && threadIdx.x < 8) a.xch_flags[((size_t)(cluster_id * 2 + (threadIdx.x >> 2)) * CL + rank) * 4 + (threadIdx.x & 3)] = 0u;
     if (warp == 1) tmem_dealloc(tbase, Cfg::kTmemCols);
 }
 
@@ -665,34 +756,46 @@ static int set_smem(KernelT kernel, int bytes) {
     return OSB_OK;
 }
 
-template <int BN, int NCHUNK, int CL, int NBUF, int SA, int SB>
-static int launch_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
-                      cudaStream_t st) {
-    using Cfg = FwdCfg<BN, NCHUNK, CL, NBUF, SA, SB>;
+template <int BN, int CL, int STAGES, int EW, bool HAS_BIAS, bool WANT_PRED>
+static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, __nv_bfloat16* dz, int64_t lddz, const FwdArgs& a,
+                        cudaStream_t st) {
+    using Cfg = FwdCfg<BN, CL, STAGES, EW>;
     const int n_tiles = (a.B + BM - 1) / BM;
-    int sms = sm_count();
-    int clusters = sms / CL;
-    if (clusters > n_tiles) clusters = n_tiles;
-    if (clusters < 1) clusters = 1;
+    auto k = head_fwd_kernel<BN, CL, STAGES, EW, HAS_BIAS, WANT_PRED>;
+    int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * CL);
-    cfg.blockDim = dim3(kThreads);
+    cfg.gridDim = dim3(sm_count() / CL * CL);
+    cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (a.bias) {
-        auto k = head_fwd_kernel<BN, NCHUNK, CL, NBUF, SA, SB, true>;
-        int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
-        OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a));
-    } else {
-        auto k = head_fwd_kernel<BN, NCHUNK, CL, NBUF, SA, SB, false>;
-        int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
-        OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a));
+    // persistent kernel: one wave of clusters.  Clusters must sit inside one GPC, so fewer than SMs/CL may be
+    // co-resident (a 4-CTA cluster strands ~16 of the 148 SMs); ask the runtime once per configuration.
+    static int resident = 0;
+    if (resident == 0) {
+        int n = 0;
+        if (CL > 1 && cudaOccupancyMaxActiveClusters(&n, k, &cfg) == cudaSuccess && n > 0) resident = n;
+        else { cudaGetLastError(); resident = sm_count() / CL; }
     }
+    int clusters = resident;
+    if (clusters > n_tiles) clusters = n_tiles;
+    if (clusters < 1) clusters = 1;
+    cfg.gridDim = dim3(clusters * CL);
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, dz, lddz, a));
     return OSB_OK;
+}
+
+template <int BN, int CL, int STAGES, int EW>
+static int launch_fwd(const CUtensorMap& tx, const CUtensorMap& tw, __nv_bfloat16* dz, int64_t lddz, const FwdArgs& a,
+                      cudaStream_t st) {
+    const bool pred = a.row_pred || a.row_pmax_all;
+    if (a.bias) return pred ? launch_fwd_k<BN, CL, STAGES, EW, true, true>(tx, tw, dz, lddz, a, st)
+                            : launch_fwd_k<BN, CL, STAGES, EW, true, false>(tx, tw, dz, lddz, a, st);
+    return pred ? launch_fwd_k<BN, CL, STAGES, EW, false, true>(tx, tw, dz, lddz, a, st)
+                : launch_fwd_k<BN, CL, STAGES, EW, false, false>(tx, tw, dz, lddz, a, st);
 }
 
 static int fwd_box_rows(int C) { return C <= 128 ? 128 : 256; }
@@ -703,12 +806,14 @@ static int fwd_box_rows(int C) { return C <= 128 ? 128 : 256; }
 using namespace osb;
 using namespace osb::head;
 
-static inline int64_t round_up8(int64_t v) { return (v + 7) / 8 * 8; }
+static long long* g_trace = nullptr;
+// developer hook (not part of the public header): device buffer of [grid][64] int64 clock stamps, or NULL
+extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<long long*>(p); }
 
 extern "C" size_t osb_head_workspace_bytes(int64_t B, int K, int C) {
     if (B < 0 || K <= 0 || C <= 0) return 0;
     const int s = dw_splits((int)B, K, C);
-    return kHeadTicketBytes + sizeof(double) * kMaxPartials + align_up((size_t)s * C * K * sizeof(float), 256) + 256;
+    return kWsOffDw + align_up((size_t)s * C * K * sizeof(float), 256) + 256;
 }
 
 #define OSB_TMAP(call, what)                                                              \
@@ -746,12 +851,10 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
                 "osb_head_forward: x, w and dz must be 16-byte aligned");
     OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "osb_head_forward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    CUtensorMap tx, tw, tdz;
+    CUtensorMap tx, tw;
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, BM), "x");
     OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, fwd_box_rows(C)), "w");
-    // without a dz buffer the store map is never used; point it at x so the encode stays valid
-    if (dz) OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 32), "dz");
-    else tdz = tx;
+    __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dz);
     FwdArgs a;
     a.bias = bias; a.y = y; a.class_w = class_w; a.B = (int)B; a.K = K; a.C = C; a.variant = variant;
     a.t_uniform = (float)(unk_weight / (double)C);
@@ -760,11 +863,15 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.row_ptgt = row_ptgt; a.row_pmax = row_pmax; a.row_pmax_all = row_pmax_all; a.row_pred = row_pred;
     a.write_dz = dz ? 1 : 0;
     a.ticket = reinterpret_cast<unsigned int*>(ws);
-    a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kHeadTicketBytes);
-    if (C <= 128) return launch_fwd<128, 1, 1, 2, 4, 4>(tx, tw, tdz, a, st);
-    if (C <= 256) return launch_fwd<256, 1, 1, 2, 3, 3>(tx, tw, tdz, a, st);
-    if (C <= 512) return launch_fwd<256, 2, 1, 1, 3, 4>(tx, tw, tdz, a, st);
-    return launch_fwd<256, 2, 2, 1, 3, 4>(tx, tw, tdz, a, st);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kWsOffPartials);
+    a.xch_flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffFlags);
+    a.xch_stats = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffStats);
+    a.trace = g_trace;
+    if (C <= 128) return launch_fwd<128, 1, 6, 2>(tx, tw, dzp, lddz, a, st);
+    if (C <= 256) return launch_fwd<256, 1, 4, 2>(tx, tw, dzp, lddz, a, st);
+    if (C <= 512) return launch_fwd<256, 2, 4, 2>(tx, tw, dzp, lddz, a, st);
+    if (C <= 768) return launch_fwd<256, 3, 4, 2>(tx, tw, dzp, lddz, a, st);
+    return launch_fwd<256, 4, 4, 2>(tx, tw, dzp, lddz, a, st);
 }
 
 extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
@@ -803,8 +910,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         if (rc) return rc;
         const int splits = dw_splits((int)B, K, C);
         const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
-        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kHeadTicketBytes + sizeof(double) * kMaxPartials);
-        partials = reinterpret_cast<float*>(align_up((size_t)partials, 256));
+        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
         head_dw_kernel<<<units, kThreads, kDwSmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
         OSB_LAUNCH_CHECK();
         const size_t n4 = (size_t)C * K / 4;

@@ -87,8 +87,7 @@ loss_rows_kernel(const LossArgs a) {
         const int64_t y = a.y[row];
         const RowMode rm = classify_row(a.variant, y, C, a.ignore_index, a.class_w, a.t_uniform * (float)C);
 
-        float v[VPT > 0 ? VPT : 1];
-        if constexpr (VPT == 0) v[0] = 0.f;
+        float v[VPT > 0 ? VPT : 1] = {};
         auto col = [&](int k) -> float {
             if constexpr (VPT > 0) return v[k];
             else { int c = lane + 32 * k; return c < C ? to_float<T>(zr[c]) : -INFINITY; }

@@ -66,11 +66,12 @@ class HeadPlan:
         if den_scale_hook is not None:
             den_scale_hook(self.den)
 
-    def forward(self, x, w, y, bias=None, write_dz=True):
+    def forward(self, x, w, y, bias=None, write_dz=True, want_pred=True):
         L.call("osb_head_forward", L.ptr(x), self.K, L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(self.class_w),
                self.B, self.K, self.C, self.variant, self.unk_weight, self.ignore_index, L.ptr(self.den), self.valid_cols,
-               L.ptr(self.loss_num), L.ptr(self.loss), L.ptr(self.p_target), L.ptr(self.p_max), L.ptr(self.p_max_all),
-               L.ptr(self.pred), L.ptr(self.dz) if write_dz else None, self.lddz,
+               L.ptr(self.loss_num), L.ptr(self.loss), L.ptr(self.p_target), L.ptr(self.p_max),
+               L.ptr(self.p_max_all) if want_pred else None, L.ptr(self.pred) if want_pred else None,
+               L.ptr(self.dz) if write_dz else None, self.lddz,
                L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
     def backward_dx(self, x, w, gscale=None):

@@ -1,0 +1,35 @@
+"""Developer tool: per-tile clock stamps of head_fwd_kernel (MMA thread and one epilogue thread)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes, numpy as np, torch
+from openset_imagenet_b200 import _lib as L
+from openset_imagenet_b200.functional import HeadPlan
+from oracle import oracle as O
+dev = torch.device("cuda:0")
+B, K, C = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (16384, 2048, 1000)))
+x = torch.randn(B, K, device=dev).bfloat16()
+w = (torch.randn(C, K, device=dev) / K ** 0.5).bfloat16()
+y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=1), device=dev)
+plan = HeadPlan(B, K, C, device=dev)
+lib = L.load()
+lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
+trace = torch.zeros(512, 64, dtype=torch.int64, device=dev)
+plan.label_stats(y)
+for _ in range(3): plan.forward(x, w, y)
+torch.cuda.synchronize()
+lib.osb_debug_set_head_trace(trace.data_ptr())
+plan.forward(x, w, y, write_dz=len(sys.argv) <= 4)
+torch.cuda.synchronize()
+lib.osb_debug_set_head_trace(None)
+t = trace.cpu().numpy()
+names = ["mma_start", "first_A_full", "mma_issued", "epi_tfull", "sweepA_done", "xchg_done", "sweepB_done"]
+gbase = t[:, 0][t[:, 0] > 0].min()
+nodz = len(sys.argv) > 4
+for cta in (0, 1, 2, 3, 4, 5, 130, 131):
+    row = t[cta]
+    if row[0] == 0 and row[3] == 0: continue
+    base = gbase
+    for it in range(4):
+        r = row[it * 8: it * 8 + 7]
+        if r.max() == 0: continue
+        print(f"cta {cta:3d} tile#{it}: " + "  ".join(f"{n}={int(v - base):7d}" for n, v in zip(names, r)))
