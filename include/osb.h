@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OSB_ABI_VERSION 1
+#define OSB_ABI_VERSION 2
 
 /* status codes */
 #define OSB_OK             0
@@ -138,37 +138,40 @@ int osb_confidence(const float* scores, int64_t ld, const int64_t* y, int64_t N,
                    double* sums, int64_t* counts, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- OSCR (util.py:90-122) ----------------------------------------------------------------- *
- * Stage A  osb_oscr_rowreduce: one pass over scores [N, ld] float32 (util.py:100-111):
- *   keys[3*N] uint32, three segments of N order-preserving float keys, 0xFFFFFFFF where absent:
- *     [0,N)   target score of every known row (gt >= 0)                 -> thresholds
- *     [N,2N)  target score of known rows with argmax == gt              -> CCR counts
- *     [2N,3N) row max of rows with gt == unk_label                      -> FPR counts
- *   totals[4] int64 {n_known, n_correct, n_unk, n_bad (known label >= C)}
- * Stage B  osb_oscr_sort: LSD radix sort (8-bit digits, warp-level match ranking, single-pass
- *   chained-scan scatter) of `nseg` segments (segment s starts at keys + s*n and holds seg_len[s] <= n
- *   keys), in place (keys_alt [nseg*n] is scratch).
- * Stage C  osb_oscr_thresholds: unique known keys of the sorted segment 0 (np.unique, util.py:113);
- *   taus[j] (float32) for j < n_unique, meta[0] = n_unique.  The largest is dropped by the caller
- *   (n_thresholds = max(n_unique-1, 0)).
- * Stage D  osb_oscr_counts: for every threshold, #correct-known > tau and #unk > tau (strict,
- *   util.py:114,117) from the sorted segments of THIS shard: ccr_cnt/fpr_cnt int64 [n_unique].
- * osb_oscr runs A-D on one GPU and also writes ccr/fpr = counts / totals as float64.
+ * RECORD = (uint64) key << 32 | type.  key = order-preserving uint32 image of a float32 score
+ * (-0.0 == +0.0); type 0 = known row, arg-max != label; 1 = known row, arg-max == label (util.py:114);
+ * 2 = row labelled unk_label (util.py:102); 3 = padding, ignored.
+ * Stage A  osb_oscr_records: the one pass over scores [N, ld] float32 (util.py:100-111).  Appends one
+ *   record per known row (key = target score) to rec_known and one per unk row (key = row max) to
+ *   rec_unk, both compacted, in no particular order, capacity N each.
+ *   totals[4] int64 (zeroed by the call) {n_known, n_correct, n_unk, n_bad (known label >= C)};
+ *   totals[0] / totals[2] are the record counts of rec_known / rec_unk.
+ *   osb_oscr_records_from_stats is the compact-input variant: rows already reduced by the fused head to
+ *   (p_target, p_max_all, pred) (osb_head_forward row_* outputs).
+ * Stage B  osb_oscr_curve: stable LSD radix sort of rec_a[0..n_a) ++ rec_b[0..n_b) by key and one scan.
+ *   Every run of equal keys holding a known record is a threshold (np.unique, util.py:113): taus[j]
+ *   float32 ascending, ccr_cnt[j] / fpr_cnt[j] int64 = records of type 1 / type 2 with key > tau
+ *   (strict, util.py:114,117), optional ccr[j] / fpr[j] = counts / n_known / n_unk as float64.
+ *   Pass the unk records as rec_a and the known records as rec_b (ties must list unk records first).
+ *   n_a, n_b: DEVICE int64 scalars; cap >= n_a + n_b sizes the workspace and the outputs.
+ *   meta[5] int64 {n_unique, n_known, n_correct, n_unk, 0}.  The reference drops the largest threshold
+ *   (util.py:113): n_thresholds = max(n_unique - 1, 0), left to the caller.
+ *   Counts at a fixed threshold are additive across row shards: a shard passes its own unk records plus
+ *   ALL shards' known records (remote ones demoted to type 0), then sums ccr_cnt / fpr_cnt over shards.
+ *   ONE cooperative launch (all CTAs co-resident; grid barriers through L2).
+ * osb_oscr = A + B on one GPU (two launches); meta[4] = n_bad.  osb_oscr_ratios: counts -> float64 ratios
+ *   after a cross-shard sum.
  */
 size_t osb_oscr_workspace_bytes(int64_t N);
-int osb_oscr_rowreduce(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
-                       int64_t unk_label, uint32_t* keys, int64_t* totals, void* stream);
-size_t osb_oscr_sort_workspace_bytes(int64_t n, int nseg);
-size_t osb_oscr_thresholds_workspace_bytes(int64_t n);
-int osb_oscr_sort(uint32_t* keys, uint32_t* keys_alt, int64_t n, int nseg,
-                  const int64_t* seg_len /* device [nseg], nullable: every segment holds n keys */,
-                  void* ws, size_t ws_bytes, void* stream);
-int osb_oscr_thresholds(const uint32_t* sorted_known, int64_t n, const int64_t* n_known,
-                        uint32_t* tau_keys, float* taus, int64_t* n_unique,
-                        void* ws, size_t ws_bytes, void* stream);
-int osb_oscr_counts(const uint32_t* tau_keys, const int64_t* n_unique,
-                    const uint32_t* sorted_correct, const int64_t* n_correct,
-                    const uint32_t* sorted_unk, const int64_t* n_unk, int64_t n,
-                    int64_t* ccr_cnt, int64_t* fpr_cnt, void* stream);
+size_t osb_oscr_curve_workspace_bytes(int64_t cap);
+int osb_oscr_records(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+                     int64_t unk_label, uint64_t* rec_unk, uint64_t* rec_known, int64_t* totals, void* stream);
+int osb_oscr_records_from_stats(const float* p_target, const float* p_max_all, const int32_t* pred,
+                                const void* gt, int gt_type, int64_t N, int C, int64_t unk_label,
+                                uint64_t* rec_unk, uint64_t* rec_known, int64_t* totals, void* stream);
+int osb_oscr_curve(const uint64_t* rec_a, const int64_t* n_a, const uint64_t* rec_b, const int64_t* n_b, int64_t cap,
+                   float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt, double* ccr /* nullable */, double* fpr /* nullable */,
+                   int64_t* meta, void* ws, size_t ws_bytes, void* stream);
 int osb_oscr_ratios(const int64_t* ccr_cnt, const int64_t* fpr_cnt, const int64_t* n_unique,
                     const int64_t* n_known, const int64_t* n_unk, int64_t n,
                     double* ccr, double* fpr, void* stream);

@@ -14,6 +14,7 @@ import torch
 
 from . import _build
 
+ABI_VERSION = 2
 OK, ERR_ARG, ERR_SHAPE, ERR_WORKSPACE, ERR_CUDA, ERR_ARCH = 0, -1, -2, -3, -4, -5
 ENTROPIC, SOFTMAX, GARBAGE = 0, 1, 2
 F32, BF16 = 0, 1
@@ -38,12 +39,10 @@ SIGNATURES = {
     "osb_confidence_workspace_bytes": (_sz, [_i64]),
     "osb_confidence": (_i, [_p, _i64, _p, _i64, _i, _f, _i64, _i, _p, _p, _p, _sz, _p]),
     "osb_oscr_workspace_bytes": (_sz, [_i64]),
-    "osb_oscr_rowreduce": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _p, _p, _p]),
-    "osb_oscr_sort_workspace_bytes": (_sz, [_i64, _i]),
-    "osb_oscr_thresholds_workspace_bytes": (_sz, [_i64]),
-    "osb_oscr_sort": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
-    "osb_oscr_thresholds": (_i, [_p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
-    "osb_oscr_counts": (_i, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "osb_oscr_curve_workspace_bytes": (_sz, [_i64]),
+    "osb_oscr_records": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _p, _p, _p, _p]),
+    "osb_oscr_records_from_stats": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i64, _p, _p, _p, _p]),
+    "osb_oscr_curve": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "osb_oscr_ratios": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "osb_oscr": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "osb_ccr_at_fpr": (_i, [_p, _p, _p, _i64, _p, _i, _p, _p, _p, _p]),
@@ -78,7 +77,7 @@ def load() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
-        if lib.osb_abi_version() != 1:
+        if lib.osb_abi_version() != ABI_VERSION:
             raise RuntimeError("libosb ABI version mismatch; rebuild with python -m openset_imagenet_b200._build --force")
         _lib = lib
     return _lib

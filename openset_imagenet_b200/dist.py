@@ -8,9 +8,10 @@ script/train_all.py:96-118); what is exchanged here follows from the arithmetic:
   all-reduced double for the softmax / garbage variants.  After backward ONE all-reduce(sum) of the
   fp32 [dW | db | loss_num] buffer makes every rank hold the full-batch gradient; dX stays local.
 * OSCR: stage A (97 % of the bytes) shards by rows.  Thresholds are the global set of unique known
-  target scores, so the known keys are all-gathered (4 B per known sample); every rank derives the
-  identical threshold list, counts its own shard against it, and ONE all-reduce(sum) of the int64
-  counts merges the shards.  Counts at a fixed threshold are additive across shards, so the result is
+  target scores, so the known records are all-gathered (8 B per sample slot); every rank sorts its own
+  unk records together with ALL known records (remote ones demoted to "threshold only"), derives the
+  identical threshold list with its own counts, and ONE all-reduce(sum) of the int64 counts merges the
+  shards.  Counts at a fixed threshold are additive across shards, so the result is
   bit-identical to the single-GPU one.
 
 All of this works on any backend: the CPU tests run the control flow with gloo (world size 2) on fake
@@ -96,24 +97,34 @@ class ShardedHead:
 # ------------------------------------------------------------------------------------------------
 # OSCR
 # ------------------------------------------------------------------------------------------------
-def merge_counts(ccr_cnt: torch.Tensor, fpr_cnt: torch.Tensor, totals: torch.Tensor, group=None):
-    """The "single small all-reduce" of the sharded OSCR: int64 [ccr counts | fpr counts | totals]."""
+_TYPE_MASK = 3
+_SKIP_RECORD = -1            # int64 view of key 0xFFFFFFFF | type 3: a padding record the scan ignores
+
+
+def merge_counts(ccr_cnt: torch.Tensor, fpr_cnt: torch.Tensor, group=None):
+    """The "single small all-reduce" of the sharded OSCR: int64 [ccr counts | fpr counts]."""
     n = ccr_cnt.numel()
-    buf = torch.cat([ccr_cnt, fpr_cnt, totals])
+    buf = torch.cat([ccr_cnt, fpr_cnt])
     _, ws = world()
     if ws > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return buf[:n], buf[n:2 * n], buf[2 * n:]
+    return buf[:n], buf[n:]
 
 
-def gather_known_keys(keys_known: torch.Tensor, n_local: int, group=None) -> torch.Tensor:
-    """All-gather the fixed-size (absent-key padded) known-key segment of every shard."""
-    _, ws = world()
+def gather_known_records(rec_known: torch.Tensor, rank: int, ws: int, group=None) -> torch.Tensor:
+    """All-gather the fixed-size (skip-padded) known-record array of every shard and demote the remote
+    shards' records to "threshold only" (type 0): they define thresholds everywhere but are counted only by
+    the shard that owns them.  Works on any backend (int64 view of the 8-byte records)."""
     if ws == 1:
-        return keys_known
-    out = torch.empty(ws * n_local, dtype=keys_known.dtype, device=keys_known.device)
-    dist.all_gather_into_tensor(out, keys_known.contiguous(), group=group)
-    return out
+        return rec_known
+    n = rec_known.numel()
+    out = torch.empty(ws * n, dtype=rec_known.dtype, device=rec_known.device)
+    dist.all_gather_into_tensor(out, rec_known.contiguous(), group=group)
+    v = out.view(ws, n)
+    remote = torch.ones(ws, 1, dtype=torch.bool, device=out.device)
+    remote[rank] = False
+    keep = ((v & _TYPE_MASK) == _TYPE_MASK) | ~remote          # padding stays padding; local rows keep their type
+    return torch.where(keep, v, v & ~_TYPE_MASK).view(-1)
 
 
 def calculate_oscr_sharded(gt, scores, unk_label=-1, group=None):
@@ -132,37 +143,30 @@ def calculate_oscr_sharded(gt, scores, unk_label=-1, group=None):
     g = g.contiguous()
     n, c = s.shape
     st = L.stream_ptr(dev)
+    cap = max(ws * n + n, 1)
     with torch.cuda.device(dev):
-        keys = torch.empty(3 * n, dtype=torch.int32, device=dev)
-        alt = torch.empty(max(3 * n, ws * n), dtype=torch.int32, device=dev)
+        rec_unk = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        rec_known = torch.full((max(n, 1),), _SKIP_RECORD, dtype=torch.int64, device=dev)
         totals = torch.zeros(4, dtype=torch.int64, device=dev)
-        L.call("osb_oscr_rowreduce", L.ptr(s), s.stride(0), L.ptr(g), _LABEL_TYPES[g.dtype], n, c, int(unk_label),
-               L.ptr(keys), L.ptr(totals), st)
-        # local sort of the two count segments; global sort of the gathered threshold segment
-        sws = torch.zeros(L.size("osb_oscr_sort_workspace_bytes", max(n, 1), 2), dtype=torch.uint8, device=dev)
-        L.call("osb_oscr_sort", L.ptr(keys[n:]), L.ptr(alt), n, 2, None, L.ptr(sws), sws.numel(), st)
-        gk = gather_known_keys(keys[:n], n, group).clone()
-        ng = gk.numel()
-        gws = torch.zeros(L.size("osb_oscr_sort_workspace_bytes", max(ng, 1), 1), dtype=torch.uint8, device=dev)
-        galt = torch.empty(ng, dtype=torch.int32, device=dev)
-        L.call("osb_oscr_sort", L.ptr(gk), L.ptr(galt), ng, 1, None, L.ptr(gws), gws.numel(), st)
+        L.call("osb_oscr_records", L.ptr(s), s.stride(0) if n else c, L.ptr(g), _LABEL_TYPES[g.dtype], n, c, int(unk_label),
+               L.ptr(rec_unk), L.ptr(rec_known), L.ptr(totals), st)
+        rec_b = gather_known_records(rec_known, rank, ws, group)
+        n_b = torch.tensor([rec_b.numel()], dtype=torch.int64, device=dev)
+        taus = torch.empty(cap, dtype=torch.float32, device=dev)
+        ccr_cnt = torch.zeros(cap, dtype=torch.int64, device=dev)
+        fpr_cnt = torch.zeros(cap, dtype=torch.int64, device=dev)
+        meta = torch.zeros(5, dtype=torch.int64, device=dev)
+        cws = L.workspace("oscr_curve", L.size("osb_oscr_curve_workspace_bytes", cap), dev)
+        L.call("osb_oscr_curve", L.ptr(rec_unk), L.ptr(totals[2:3]), L.ptr(rec_b), L.ptr(n_b), cap,
+               L.ptr(taus), L.ptr(ccr_cnt), L.ptr(fpr_cnt), None, None, L.ptr(meta), L.ptr(cws), cws.numel(), st)
+        # every rank derived the same thresholds; the counts are per shard: ONE all-reduce merges them
         tot_g = totals.clone()
         if ws > 1:
             dist.all_reduce(tot_g, op=dist.ReduceOp.SUM, group=group)
-        tau_keys = torch.empty(max(ng, 1), dtype=torch.int32, device=dev)
-        taus = torch.empty(max(ng, 1), dtype=torch.float32, device=dev)
-        n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
-        uws = torch.zeros(L.size("osb_oscr_thresholds_workspace_bytes", max(ng, 1)), dtype=torch.uint8, device=dev)
-        L.call("osb_oscr_thresholds", L.ptr(gk), ng, L.ptr(tot_g[0:1]), L.ptr(tau_keys), L.ptr(taus), L.ptr(n_unique),
-               L.ptr(uws), uws.numel(), st)
-        ccr_cnt = torch.zeros(max(ng, 1), dtype=torch.int64, device=dev)
-        fpr_cnt = torch.zeros(max(ng, 1), dtype=torch.int64, device=dev)
-        L.call("osb_oscr_counts", L.ptr(tau_keys), L.ptr(n_unique), L.ptr(keys[n:]), L.ptr(totals[1:2]),
-               L.ptr(keys[2 * n:]), L.ptr(totals[2:3]), ng, L.ptr(ccr_cnt), L.ptr(fpr_cnt), st)
-        ccr_cnt, fpr_cnt, _ = merge_counts(ccr_cnt, fpr_cnt, torch.zeros(0, dtype=torch.int64, device=dev), group)
-        ccr = torch.empty(max(ng, 1), dtype=torch.float64, device=dev)
-        fpr = torch.empty(max(ng, 1), dtype=torch.float64, device=dev)
-        L.call("osb_oscr_ratios", L.ptr(ccr_cnt), L.ptr(fpr_cnt), L.ptr(n_unique), L.ptr(tot_g[0:1]), L.ptr(tot_g[2:3]),
-               ng, L.ptr(ccr), L.ptr(fpr), st)
-    meta = torch.cat([n_unique, tot_g])
-    return ccr, fpr, ccr_cnt, fpr_cnt, taus, meta
+        ccr_cnt, fpr_cnt = merge_counts(ccr_cnt, fpr_cnt, group)
+        ccr = torch.empty(cap, dtype=torch.float64, device=dev)
+        fpr = torch.empty(cap, dtype=torch.float64, device=dev)
+        L.call("osb_oscr_ratios", L.ptr(ccr_cnt), L.ptr(fpr_cnt), L.ptr(meta[0:1]), L.ptr(tot_g[0:1]), L.ptr(tot_g[2:3]),
+               cap, L.ptr(ccr), L.ptr(fpr), st)
+    meta_g = torch.cat([meta[0:1], tot_g])
+    return ccr, fpr, ccr_cnt, fpr_cnt, taus, meta_g

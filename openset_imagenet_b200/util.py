@@ -85,6 +85,38 @@ def calculate_oscr_device(gt, scores, unk_label=-1, device=None) -> OscrDeviceRe
     return OscrDeviceResult(taus, ccr_cnt, fpr_cnt, ccr, fpr, meta)
 
 
+def calculate_oscr_from_stats_device(gt, p_target, p_max_all, pred, num_classes, unk_label=-1) -> OscrDeviceResult:
+    """Compact-input OSCR: every row already reduced (by the fused head, ``HeadStats``) to the softmax
+    probability of its label, its row maximum and its arg-max, so no [N, C] score matrix exists.  Same
+    result as ``calculate_oscr_device`` on the scores those statistics were taken from."""
+    dev = L.require_cuda(p_target, p_max_all, pred, gt)
+    g = gt if gt.dtype in _LABEL_TYPES else gt.to(torch.int64)
+    g = g.contiguous()
+    pt, pm, pr = p_target.float().contiguous(), p_max_all.float().contiguous(), pred.to(torch.int32).contiguous()
+    N = g.shape[0]
+    if not (pt.shape == pm.shape == pr.shape == g.shape):
+        raise ValueError("gt, p_target, p_max_all and pred must all be [samples]")
+    with torch.cuda.device(dev):
+        cap = max(N, 1)
+        rec_unk = torch.empty(cap, dtype=torch.int64, device=dev)
+        rec_known = torch.empty(cap, dtype=torch.int64, device=dev)
+        totals = torch.empty(4, dtype=torch.int64, device=dev)
+        taus = torch.empty(cap, dtype=torch.float32, device=dev)
+        ccr_cnt = torch.empty(cap, dtype=torch.int64, device=dev)
+        fpr_cnt = torch.empty(cap, dtype=torch.int64, device=dev)
+        ccr = torch.empty(cap, dtype=torch.float64, device=dev)
+        fpr = torch.empty(cap, dtype=torch.float64, device=dev)
+        meta = torch.zeros(5, dtype=torch.int64, device=dev)
+        st = L.stream_ptr(dev)
+        L.call("osb_oscr_records_from_stats", L.ptr(pt), L.ptr(pm), L.ptr(pr), L.ptr(g), _LABEL_TYPES[g.dtype], N,
+               int(num_classes), int(unk_label), L.ptr(rec_unk), L.ptr(rec_known), L.ptr(totals), st)
+        ws = L.workspace("oscr_curve", L.size("osb_oscr_curve_workspace_bytes", cap), dev)
+        L.call("osb_oscr_curve", L.ptr(rec_unk), L.ptr(totals[2:3]), L.ptr(rec_known), L.ptr(totals[0:1]), cap,
+               L.ptr(taus), L.ptr(ccr_cnt), L.ptr(fpr_cnt), L.ptr(ccr), L.ptr(fpr), L.ptr(meta), L.ptr(ws), ws.numel(), st)
+        meta[4] = totals[3]
+    return OscrDeviceResult(taus, ccr_cnt, fpr_cnt, ccr, fpr, meta)
+
+
 def calculate_oscr(gt, scores, unk_label=-1):
     """Drop-in for ``openset_imagenet.util.calculate_oscr``.
 

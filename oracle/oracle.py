@@ -256,6 +256,40 @@ def oscr_counts(gt, scores, unk_label=-1):
     return taus, ccr_cnt, fpr_cnt, n_kn, n_unk
 
 
+def float_keys(v):
+    """Order-preserving uint32 image of float32 values (-0.0 == +0.0), as the kernels build it."""
+    b = np.ascontiguousarray(v, dtype=np.float32).view(np.uint32).copy()
+    b[b == np.uint32(0x80000000)] = 0
+    neg = (b & np.uint32(0x80000000)) != 0
+    return np.where(neg, ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def oscr_records(gt, scores, unk_label=-1):
+    """The two record arrays stage A of the CUDA path emits (include/osb.h): (rec_unk, rec_known) uint64,
+    record = key << 32 | type, type 0 known & wrong, 1 known & correct (util.py:114), 2 unk (util.py:102)."""
+    gt = np.asarray(gt).astype(int)
+    scores = np.asarray(scores)
+    known, unk = gt >= 0, gt == unk_label
+    pred, top = scores.argmax(axis=1), scores.max(axis=1)
+    hit = (pred[known] == gt[known]).astype(np.uint64)
+    rec_known = (float_keys(scores[known, gt[known]]).astype(np.uint64) << np.uint64(32)) | hit
+    rec_unk = (float_keys(top[unk]).astype(np.uint64) << np.uint64(32)) | np.uint64(2)
+    return rec_unk, rec_known
+
+
+def oscr_curve_from_records(rec_a, rec_b):
+    """numpy stand-in for osb_oscr_curve: thresholds (ALL unique known keys, as float32) and the counts of type-1 /
+    type-2 records with key > threshold.  Type-3 records are padding."""
+    rec = np.concatenate([np.asarray(rec_a, dtype=np.uint64), np.asarray(rec_b, dtype=np.uint64)])
+    key, typ = (rec >> np.uint64(32)).astype(np.uint32), (rec & np.uint64(3)).astype(np.int64)
+    tau_keys = np.unique(key[typ < 2])
+    cts, ums = np.sort(key[typ == 1]), np.sort(key[typ == 2])
+    ccr_cnt = (len(cts) - np.searchsorted(cts, tau_keys, side="right")).astype(np.int64)
+    fpr_cnt = (len(ums) - np.searchsorted(ums, tau_keys, side="right")).astype(np.int64)
+    b = np.where(tau_keys & np.uint32(0x80000000), tau_keys & np.uint32(0x7FFFFFFF), ~tau_keys).astype(np.uint32)
+    return b.view(np.float32), ccr_cnt, fpr_cnt
+
+
 def calculate_oscr(gt, scores, unk_label=-1, quadratic=False):
     """(ccr, fpr) float64 arrays exactly as util.py:90-122 returns them."""
     fn = oscr_counts_quadratic if quadratic else oscr_counts

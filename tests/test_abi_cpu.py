@@ -34,7 +34,7 @@ def test_library_exports_every_symbol():
     lib = _lib.load()
     for name in _header_prototypes():
         assert hasattr(lib, name), name
-    assert lib.osb_abi_version() == 1
+    assert lib.osb_abi_version() == _lib.ABI_VERSION
 
 
 def test_library_is_sm100a_only():

@@ -49,6 +49,144 @@ def test_oscr_random_bit_exact(N, C, unk):
     np.testing.assert_array_equal(fpr, o_fpr)
 
 
+def test_oscr_strided_wide_and_unaligned_inputs():
+    """Row pitch > C, very wide rows and a misaligned base pointer take the non-bulk-copy path of stage A."""
+    from openset_imagenet_b200.util import calculate_oscr_device
+    gt, s = O.make_oscr_case(3000, 37, seed=21)
+    o = O.oscr_counts(gt, s, -1)
+    wide = torch.zeros(3000, 64, device="cuda")
+    wide[:, :37] = torch.tensor(s)
+    flat = torch.zeros(3000 * 37 + 1, device="cuda")
+    flat[1:] = torch.tensor(s).reshape(-1)
+    for s_in in (wide[:, :37], flat[1:].view(3000, 37)):
+        r = calculate_oscr_device(torch.tensor(gt, device="cuda"), s_in, -1)
+        n = int(r.meta[0]) - 1
+        np.testing.assert_array_equal(r.taus[:n].cpu().numpy(), o[0])
+        np.testing.assert_array_equal(r.ccr_cnt[:n].cpu().numpy(), o[1])
+        np.testing.assert_array_equal(r.fpr_cnt[:n].cpu().numpy(), o[2])
+    gt, s = O.make_oscr_case(300, 5000, seed=22)            # 20 KB rows: wider than a bulk-copy stage
+    ccr, fpr = _calc(gt, s, -2)
+    o_ccr, o_fpr = O.calculate_oscr(gt, s, -2)
+    np.testing.assert_array_equal(ccr, o_ccr)
+    np.testing.assert_array_equal(fpr, o_fpr)
+
+
+def test_oscr_records_stage_multiset():
+    """Stage A alone: the compacted records are exactly the oracle's (key, type) multiset."""
+    from openset_imagenet_b200 import _lib as L
+    N, C = 50_000, 116
+    gt, s = O.make_oscr_case(N, C, seed=5)
+    dev = torch.device("cuda")
+    st, gtt = torch.tensor(s, device=dev), torch.tensor(gt, device=dev)
+    recu = torch.empty(N, dtype=torch.int64, device=dev)
+    reck = torch.empty(N, dtype=torch.int64, device=dev)
+    tot = torch.empty(4, dtype=torch.int64, device=dev)
+    L.call("osb_oscr_records", L.ptr(st), C, L.ptr(gtt), L.LABEL_I64, N, C, -1, L.ptr(recu), L.ptr(reck), L.ptr(tot), L.stream_ptr(dev))
+    n_kn, n_ok, n_unk, n_bad = tot.tolist()
+    kn = gt >= 0
+    pred = s.argmax(1)
+    assert (n_kn, n_unk, n_bad) == (int(kn.sum()), int((gt == -1).sum()), 0)
+    assert n_ok == int((pred[kn] == gt[kn]).sum())
+
+    def recs(vals, types):
+        keys = vals.view(np.uint32).astype(np.uint64) | np.uint64(0x80000000)      # scores are >= 0
+        return np.sort((keys << np.uint64(32)) | types.astype(np.uint64))
+
+    want_k = recs(s[kn, gt[kn]], (pred[kn] == gt[kn]))
+    want_u = recs(s[gt == -1].max(1), np.full(n_unk, 2))
+    np.testing.assert_array_equal(np.sort(reck[:n_kn].cpu().numpy().view(np.uint64)), want_k)
+    np.testing.assert_array_equal(np.sort(recu[:n_unk].cpu().numpy().view(np.uint64)), want_u)
+
+
+@pytest.mark.parametrize("shards", [2, 3])
+def test_oscr_shard_merge_is_bit_exact(shards):
+    """The multi-GPU algorithm on one GPU: per-shard records, 'all-gathered' known records with remote ones
+    demoted and skip padding, per-shard curve, summed counts == single-shard result (through the C ABI)."""
+    from openset_imagenet_b200 import _lib as L
+    from openset_imagenet_b200.util import calculate_oscr_device
+    N, C = 30_000, 31
+    n = N // shards
+    gt, s = O.make_oscr_case(n * shards, C, seed=9)
+    s[::5] = np.round(s[::5], 2)                                  # plenty of ties across shards
+    dev = torch.device("cuda")
+    stp = L.stream_ptr(dev)
+    full = calculate_oscr_device(gt, s, -1)
+    nu = int(full.meta[0])
+    rec_u, rec_k, tots = [], [], []
+    for r in range(shards):
+        st = torch.tensor(s[r * n:(r + 1) * n], device=dev)
+        gtt = torch.tensor(gt[r * n:(r + 1) * n], device=dev)
+        ru = torch.empty(n, dtype=torch.int64, device=dev)
+        rk = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        tt = torch.empty(4, dtype=torch.int64, device=dev)
+        L.call("osb_oscr_records", L.ptr(st), C, L.ptr(gtt), L.LABEL_I64, n, C, -1, L.ptr(ru), L.ptr(rk), L.ptr(tt), stp)
+        rec_u.append(ru); rec_k.append(rk); tots.append(tt)
+    cap = shards * n + n
+    ws = torch.zeros(L.size("osb_oscr_curve_workspace_bytes", cap), dtype=torch.uint8, device=dev)
+    sum_c = torch.zeros(cap, dtype=torch.int64, device=dev)
+    sum_f = torch.zeros(cap, dtype=torch.int64, device=dev)
+    for r in range(shards):
+        parts = [rk if q == r else torch.where((rk & 3) == 3, rk, rk & ~3) for q, rk in enumerate(rec_k)]
+        rec_b = torch.cat(parts)
+        n_b = torch.tensor([rec_b.numel()], dtype=torch.int64, device=dev)
+        taus = torch.empty(cap, dtype=torch.float32, device=dev)
+        cc = torch.zeros(cap, dtype=torch.int64, device=dev)
+        fc = torch.zeros(cap, dtype=torch.int64, device=dev)
+        meta = torch.zeros(5, dtype=torch.int64, device=dev)
+        L.call("osb_oscr_curve", L.ptr(rec_u[r]), L.ptr(tots[r][2:3]), L.ptr(rec_b), L.ptr(n_b), cap,
+               L.ptr(taus), L.ptr(cc), L.ptr(fc), None, None, L.ptr(meta), L.ptr(ws), ws.numel(), stp)
+        assert int(meta[0]) == nu
+        np.testing.assert_array_equal(taus[:nu].cpu().numpy(), full.taus[:nu].cpu().numpy())
+        sum_c += cc; sum_f += fc
+    np.testing.assert_array_equal(sum_c[:nu].cpu().numpy(), full.ccr_cnt[:nu].cpu().numpy())
+    np.testing.assert_array_equal(sum_f[:nu].cpu().numpy(), full.fpr_cnt[:nu].cpu().numpy())
+
+
+def test_oscr_from_head_statistics():
+    """Compact-input variant: (p_target, p_max_all, pred) per row instead of the score matrix."""
+    from openset_imagenet_b200.util import calculate_oscr_device, calculate_oscr_from_stats_device
+    N, C = 40_000, 116
+    gt, s = O.make_oscr_case(N, C, seed=12)
+    dev = torch.device("cuda")
+    st, gtt = torch.tensor(s, device=dev), torch.tensor(gt, device=dev)
+    full = calculate_oscr_device(gtt, st, -2)
+    pmax = st.max(1).values
+    pred = torch.tensor(s.argmax(1), device=dev)                   # numpy's first arg-max
+    ptgt = st.gather(1, gtt.clamp(min=0).view(-1, 1)).view(-1)
+    r = calculate_oscr_from_stats_device(gtt, ptgt, pmax, pred, C, -2)
+    assert r.meta.tolist() == full.meta.tolist()
+    n = int(r.meta[0])
+    for a, b in ((r.taus, full.taus), (r.ccr_cnt, full.ccr_cnt), (r.fpr_cnt, full.fpr_cnt), (r.ccr, full.ccr), (r.fpr, full.fpr)):
+        np.testing.assert_array_equal(a[:n].cpu().numpy(), b[:n].cpu().numpy())
+
+
+def test_oscr_workspace_is_reusable_and_graph_capturable():
+    """Back-to-back calls on one workspace (counters must be left zero) and replay from a CUDA graph."""
+    from openset_imagenet_b200.util import calculate_oscr_device
+    gt, s = O.make_oscr_case(20_000, 116, seed=3)
+    o = O.oscr_counts(gt, s, -1)
+    dev = torch.device("cuda")
+    st, gtt = torch.tensor(s, device=dev), torch.tensor(gt, device=dev)
+    for _ in range(3):
+        r = calculate_oscr_device(gtt, st, -1)
+        n = int(r.meta[0]) - 1
+        np.testing.assert_array_equal(r.ccr_cnt[:n].cpu().numpy(), o[1])
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        r = calculate_oscr_device(gtt, st, -1)                # allocate the workspace of this stream before capture
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            r = calculate_oscr_device(gtt, st, -1)
+        for _ in range(2):
+            r.ccr_cnt.zero_()
+            graph.replay()
+            side.synchronize()
+            n = int(r.meta[0]) - 1
+            np.testing.assert_array_equal(r.ccr_cnt[:n].cpu().numpy(), o[1])
+            np.testing.assert_array_equal(r.fpr_cnt[:n].cpu().numpy(), o[2])
+
+
 def test_oscr_heavy_ties_and_special_values():
     rng = np.random.default_rng(0)
     N, C = 9000, 20

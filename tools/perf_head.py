@@ -62,15 +62,20 @@ def oscr_case(N, C):
     st = torch.tensor(s, device=dev); gtt = torch.tensor(gt, device=dev)
     stp = L.stream_ptr(dev)
     ws = torch.zeros(L.size("osb_oscr_workspace_bytes", N) + 4096, dtype=torch.uint8, device=dev)
-    keys = torch.empty(3 * N, dtype=torch.int32, device=dev); alt = torch.empty_like(keys)
+    recu = torch.empty(N, dtype=torch.int64, device=dev); reck = torch.empty(N, dtype=torch.int64, device=dev)
     totals = torch.zeros(4, dtype=torch.int64, device=dev)
-    sws = torch.zeros(L.size("osb_oscr_sort_workspace_bytes", N, 3), dtype=torch.uint8, device=dev)
-    def rr(): L.call("osb_oscr_rowreduce", st.data_ptr(), C, gtt.data_ptr(), 0, N, C, -1, keys.data_ptr(), totals.data_ptr(), stp)
-    def so(): L.call("osb_oscr_sort", keys.data_ptr(), alt.data_ptr(), N, 3, None, sws.data_ptr(), sws.numel(), stp)
+    cws = torch.zeros(L.size("osb_oscr_curve_workspace_bytes", N), dtype=torch.uint8, device=dev)
+    taus = torch.empty(N, dtype=torch.float32, device=dev)
+    cc = torch.empty(N, dtype=torch.int64, device=dev); fc = torch.empty(N, dtype=torch.int64, device=dev)
+    ccr = torch.empty(N, dtype=torch.float64, device=dev); fpr = torch.empty(N, dtype=torch.float64, device=dev)
+    meta = torch.zeros(5, dtype=torch.int64, device=dev)
+    def rr(): L.call("osb_oscr_records", st.data_ptr(), C, gtt.data_ptr(), 0, N, C, -1, recu.data_ptr(), reck.data_ptr(), totals.data_ptr(), stp)
+    def so(): L.call("osb_oscr_curve", recu.data_ptr(), totals[2:3].data_ptr(), reck.data_ptr(), totals[0:1].data_ptr(), N,
+                     taus.data_ptr(), cc.data_ptr(), fc.data_ptr(), ccr.data_ptr(), fpr.data_ptr(), meta.data_ptr(), cws.data_ptr(), cws.numel(), stp)
     def full(): calculate_oscr_device(gtt, st, -1)
     bytes_alg = N * C * 4 + N * 8
     print(f"--- oscr N={N} C={C}: algorithmic bytes {bytes_alg/1e6:.1f} MB")
-    for name, fn in [("rowreduce", rr), ("sort(3 seg)", so), ("full", full)]:
+    for name, fn in [("records (A)", rr), ("curve (B)", so), ("full", full)]:
         med, mn = timeit(fn)
         print(f"{name:16s} med {med:9.1f} us min {mn:9.1f} us | {bytes_alg/med/1e3:8.1f} GB/s-equivalent")
     # confidence
