@@ -45,9 +45,11 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // ---------------------------------------------------------------------------------------------
 // stage A
 // ---------------------------------------------------------------------------------------------
-constexpr int kRecThreads = 512;
+constexpr int kRecThreads = 256;          // two CTAs per SM: one computes while the other waits for its next chunk
 constexpr int kRecWarps = kRecThreads / 32;
-constexpr int kStageCap = 2048;          // staged records per type per CTA
+constexpr int kStageCap = 1024;          // staged records per type per CTA
+constexpr int kRecCtasPerSm = 2;
+constexpr size_t kRecStageBudget = 92 * 1024;   // bulk-copy stages per CTA (2 x (92 KB + 16.5 KB staging) fits one SM)
 constexpr int kMaxStages = 8;
 
 struct RecShared {
@@ -82,7 +84,8 @@ __device__ __forceinline__ void smem_row_split_max(const float* row, int C, int 
         head = head > C ? C : head;
     }
     const int nvec = (C - head) >> 2;
-    const int jb = lab < head ? 0 : ((lab - head) >> 2);       // aligned groups j < jb lie entirely before lab
+    const int jb = ALIGNED ? ((lab < 0 ? 0 : lab) >> 2)        // aligned groups j < jb lie entirely before lab
+                           : (lab < head ? 0 : ((lab - head) >> 2));
     head_out = head; jb_out = jb;
     if (active) {
         if (!ALIGNED) {                                         // unaligned ends, exact per-element split
@@ -95,16 +98,22 @@ __device__ __forceinline__ void smem_row_split_max(const float* row, int C, int 
             }
         }
         const float4* r4 = reinterpret_cast<const float4*>(row + head);
-        const int iters = ((C >> 2) + LPR - 1) / LPR;           // same for every row of the chunk: uniform control flow
-#pragma unroll 4
-        for (int it = 0; it < iters; ++it) {
-            const int j = sub + it * LPR;
-            if (j < nvec) {
-                const float4 v = r4[j];
-                const float t = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-                m_all = fmaxf(m_all, t);
-                m_lo = fmaxf(m_lo, j < jb ? t : -INFINITY);
-            }
+        // whole sweeps of LPR float4 need no bounds check (same trip count for every row when ALIGNED); one
+        // predicated sweep takes the remainder
+        const int full = nvec / LPR;
+        int j = sub;
+#pragma unroll 8
+        for (int it = 0; it < full; ++it, j += LPR) {
+            const float4 v = r4[j];
+            const float t = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            m_all = fmaxf(m_all, t);
+            m_lo = fmaxf(m_lo, j < jb ? t : -INFINITY);
+        }
+        if (j < nvec) {
+            const float4 v = r4[j];
+            const float t = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            m_all = fmaxf(m_all, t);
+            m_lo = fmaxf(m_lo, j < jb ? t : -INFINITY);
         }
     }
 #pragma unroll
@@ -131,10 +140,10 @@ __device__ __forceinline__ void flush_records(uint64_t* s_rec, unsigned* s_n, un
 // TMA = true : rows are contiguous (ld == C) and the base is 16-byte aligned; chunks of R rows arrive by bulk copy.
 // TMA = false: any ld / alignment / width; rows are read with 128-bit (or scalar) non-allocating loads.
 template <typename L, int LPR, bool TMA, bool ALIGNED>
-__global__ void __launch_bounds__(kRecThreads, 1)
+__global__ void __launch_bounds__(kRecThreads, kRecCtasPerSm)
 oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __restrict__ gt, int64_t N, int C,
                     int R, int S, int64_t unk_label, bool vec4,
-                    uint64_t* __restrict__ recU, uint64_t* __restrict__ recK, unsigned long long* __restrict__ totals) {
+                    uint64_t* __restrict__ recU, uint64_t* __restrict__ recK, unsigned long long* __restrict__ totals, int dbg) {
     constexpr int RPW = 32 / LPR;
     extern __shared__ __align__(128) uint8_t rec_smem[];
     const uint32_t stage_bytes = TMA ? (uint32_t)R * (uint32_t)C * 4u : 0u;
@@ -186,7 +195,7 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
                 __syncthreads();
             }
         }
-        for (int r = my_row; r - lane / LPR < rows; r += kRecWarps * RPW) {     // warp-uniform trip count
+        for (int r = my_row; r - lane / LPR < rows && !(dbg & 2); r += kRecWarps * RPW) {     // warp-uniform trip count
             const bool valid = r < rows;
             const int64_t l64 = valid ? label_as_int<L>(TMA ? slab[r] : gt[row0 + r]) : -1;
             const bool bad = valid && l64 >= C;                    // reference: IndexError at util.py:111
@@ -202,8 +211,15 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
                 if (known && sub == 0) {
                     ts = row[lab];                                 // util.py:111
                     ok = (ts > m_lo) && (ts == m);                 // first arg-max == gt (util.py:109,114) ...
-                    const int c0 = lab < head ? lab : head + 4 * jb;
-                    for (int c = c0; c < lab; ++c) ok = ok && (row[c] < ts);        // ... inside lab's own 4-element group
+                    if (ALIGNED) {                                 // ... and inside lab's own 4-element group
+                        const float4 g4 = reinterpret_cast<const float4*>(row)[lab >> 2];
+                        const int q = lab & 3;
+                        ok = ok && (q < 1 || g4.x < ts) && (q < 2 || g4.y < ts) && (q < 3 || g4.z < ts);
+                    } else {
+                        const int c0 = lab < head ? lab : head + 4 * jb;
+#pragma unroll 1
+                        for (int c = c0; c < lab; ++c) ok = ok && (row[c] < ts);
+                    }
                 }
             } else {
                 int am;
@@ -211,7 +227,7 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
                 if (am == 0x7fffffff) am = 0;                      // a row of -inf: numpy's argmax is 0
                 if (known && sub == 0) { ts = scores[(row0 + r) * ld + lab]; ok = (am == lab); }
             }
-            if (sub == 0) {
+            if (sub == 0 && !(dbg & 1)) {
                 if (known) {
                     const unsigned p = atomicAdd(&sh.nK, 1u);
                     sh.recK[p] = make_rec(float_to_key(ts), ok ? kTypeCorrect : kTypeWrong);
@@ -310,6 +326,9 @@ constexpr int kScanRows = 4;                     // thresholds, correct, unk, kn
 constexpr int kGroup = 16;                       // tiles per group of the two-level cross-tile prefix (more when T > 1024)
 constexpr int kMaxGroups = 64;                   // fixed-size group-sum table: its zero-state sits at a fixed workspace offset
 constexpr int kTraceSlots = 32;
+constexpr int kQuarters = kCvThreads / kRadix;   // 4
+constexpr int kWarpsPerQuarter = kCvWarps / kQuarters;
+static_assert(kCvThreads % kRadix == 0 && kCvWarps % kQuarters == 0, "block shape");
 
 struct CurveParams {
     const uint64_t* rec_a; const int64_t* n_a;   // logical sort input = rec_a[0..n_a) ++ rec_b[0..n_b)
@@ -331,6 +350,7 @@ struct CurveShared {
     uint64_t rec[kCvTile];                       // tile of records; in the emit phase: staged threshold keys | correct counts
     uint32_t stage_u[kCvTile];                   // emit phase: staged unk counts
     uint32_t whist[kCvWarps][kRadix];
+    uint32_t qsum[kQuarters][kRadix], qpre[kQuarters][kRadix];
     uint32_t start[kRadix];
     uint32_t goff[kRadix];
     uint32_t part[kRadix];
@@ -385,7 +405,7 @@ oscr_curve_kernel(const CurveParams p) {
     for (int pass = 0; pass < 4; ++pass) {
         const uint64_t* src = (pass & 1) ? p.buf0 : p.buf1;     // pass 0 reads rec_a ++ rec_b instead
         uint64_t* dst = (pass & 1) ? p.buf1 : p.buf0;
-        const int shift = 32 + 8 * pass;
+        const int shift = 8 * pass;                 // digit of the 32-bit key = high word of the record
         uint32_t* gs = p.gsum + (size_t)pass * kMaxGroups * kRadix;
         stamp(pass * 6 + 0);
 
@@ -393,6 +413,7 @@ oscr_curve_kernel(const CurveParams p) {
         auto load_rank = [&](int64_t t) {
             for (int i = tid; i < kCvWarps * kRadix; i += kCvThreads) (&sh.whist[0][0])[i] = 0;
             __syncthreads();
+            if (pass == 1) stamp(28);
             const int64_t base = t * tile_sz;
             const int count = (int)((n - base) < tile_sz ? (n - base) : tile_sz);
 #pragma unroll
@@ -406,14 +427,14 @@ oscr_curve_kernel(const CurveParams p) {
             for (int r = 0; r < kCvKpt; ++r) {
                 if (r < kpt) {
                     const bool valid = (wbase + r * 32 + lane) < count;
-                    const uint32_t d = (uint32_t)(rec[r] >> shift) & 0xffu;
+                    const uint32_t d = ((uint32_t)(rec[r] >> 32) >> shift) & 0xffu;
                     // lanes holding the same digit: 8 ballots (match.any costs one round per DISTINCT value in the warp)
                     unsigned peers = __ballot_sync(kFull, valid);
 #pragma unroll
                     for (int b = 0; b < 8; ++b) {
-                        const bool bit = (d >> b) & 1u;
+                        const bool bit = (d & (1u << b)) != 0u;
                         const unsigned m = __ballot_sync(kFull, bit);
-                        peers &= bit ? m : ~m;
+                        peers &= m ^ (bit ? 0u : 0xffffffffu);
                     }
                     if (!valid) peers = 1u << lane;
                     const int leader = __ffs(peers) - 1;
@@ -422,17 +443,33 @@ oscr_curve_kernel(const CurveParams p) {
                     old = __shfl_sync(kFull, old, leader);
                     rnk[r] = old + __popc(peers & ((1u << lane) - 1u));
                     __syncwarp();
+                    if (pass == 1 && r == 0) stamp(29);
                 }
             }
+            if (pass == 1) stamp(30);
             __syncthreads();
-            tile_cnt = 0;
-            if (tid < kRadix) {
+            if (pass == 1) stamp(31);
+            // exclusive scan of the per-warp digit counts over the warps: quarter q of the block takes warps
+            // [q*W, (q+1)*W) of digit tid & 255, then the quarters are chained through qpre
+            {
+                const int d = tid & (kRadix - 1), q = tid >> 8;
+                uint32_t run = 0;
 #pragma unroll
-                for (int w = 0; w < kCvWarps; ++w) {
-                    const uint32_t c = sh.whist[w][tid];
-                    sh.whist[w][tid] = tile_cnt;             // exclusive over warps
-                    tile_cnt += c;
+                for (int w = 0; w < kWarpsPerQuarter; ++w) {
+                    const uint32_t c = sh.whist[q * kWarpsPerQuarter + w][d];
+                    sh.whist[q * kWarpsPerQuarter + w][d] = run;
+                    run += c;
                 }
+                sh.qsum[q][d] = run;
+            }
+            __syncthreads();
+            {
+                const int d = tid & (kRadix - 1), q = tid >> 8;
+                uint32_t pre = 0, tot = 0;
+#pragma unroll
+                for (int qq = 0; qq < kQuarters; ++qq) { const uint32_t v = sh.qsum[qq][d]; tot += v; pre += qq < q ? v : 0u; }
+                sh.qpre[q][d] = pre;
+                tile_cnt = tid < kRadix ? tot : 0u;
             }
             return count;
         };
@@ -515,15 +552,15 @@ oscr_curve_kernel(const CurveParams p) {
                 if (r < kpt) {
                     const int idx = wbase + r * 32 + lane;
                     if (idx < my_count) {
-                        const uint32_t dd = (uint32_t)(rec[r] >> shift) & 0xffu;
-                        sh.rec[sh.start[dd] + sh.whist[warp][dd] + rnk[r]] = rec[r];
+                        const uint32_t dd = ((uint32_t)(rec[r] >> 32) >> shift) & 0xffu;
+                        sh.rec[sh.start[dd] + sh.qpre[warp / kWarpsPerQuarter][dd] + sh.whist[warp][dd] + rnk[r]] = rec[r];
                     }
                 }
             }
             __syncthreads();
             for (int i = tid; i < my_count; i += kCvThreads) {
                 const uint64_t v = sh.rec[i];
-                const uint32_t dd = (uint32_t)(v >> shift) & 0xffu;
+                const uint32_t dd = ((uint32_t)(v >> 32) >> shift) & 0xffu;
                 dst[sh.goff[dd] + (uint32_t)i] = v;
             }
             if (!single) __syncthreads();
@@ -603,14 +640,14 @@ oscr_curve_kernel(const CurveParams p) {
     stamp(25);
     grid_barrier(p.sync, bar_target, G);
     stamp(26);
-    // totals over all tiles (warp x sums row x)
+    // totals over all tiles, and the prefix of this CTA's first tile, from one sweep (warp x sums row x)
     if (warp < kScanRows) {
         const uint32_t* row = p.scanmat + (size_t)warp * tpad;
-        uint32_t acc = 0;
-        for (int64_t tt = lane; tt < T; tt += 32) acc += __ldcg(row + tt);
+        uint32_t acc = 0, pre = 0;
+        for (int64_t tt = lane; tt < T; tt += 32) { const uint32_t v = __ldcg(row + tt); acc += v; pre += tt < (int64_t)g ? v : 0u; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-        if (lane == 0) sh.tot[warp] = acc;
+        for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(kFull, acc, o); pre += __shfl_xor_sync(kFull, pre, o); }
+        if (lane == 0) { sh.tot[warp] = acc; sh.pre[warp] = pre; }
     }
     __syncthreads();
     const int64_t n_unique = sh.tot[0], n_correct = sh.tot[1], n_unk = sh.tot[2], n_known = sh.tot[3];
@@ -623,11 +660,11 @@ oscr_curve_kernel(const CurveParams p) {
         const double q = a * r;
         return fma(fma(-q, b, a), r, q);
     };
-    uint32_t wrun = 0;                    // warp x < 4: sum of row x over tiles [0, t_seen)
-    int64_t t_seen = 0;
+    uint32_t wrun = sh.pre[warp < kScanRows ? warp : 0];   // warp x < 4: sum of row x over tiles [0, t_seen)
+    int64_t t_seen = g;
     for (int64_t t = g; t < T; t += G) {
         if (!single) scan_tile(t);
-        if (warp < kScanRows) {
+        if (warp < kScanRows && t > (int64_t)g) {
             const uint32_t* row = p.scanmat + (size_t)warp * tpad;
             uint32_t acc = 0;
             for (int64_t tt = t_seen + lane; tt < t; tt += 32) acc += __ldcg(row + tt);
@@ -756,6 +793,7 @@ ccr_at_fpr_kernel(const double* __restrict__ ccr, const double* __restrict__ fpr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static int g_rec_debug = 0;      // developer hook: bit 0 = do not emit records, bit 1 = skip the row loop (timing experiments only)
 struct RecPlan { bool tma; bool aligned; int lpr; int R; int S; size_t smem; bool vec4; int grid; };
 
 template <typename L>
@@ -768,15 +806,15 @@ static RecPlan plan_records(const float* scores, int64_t ld, const L* gt, int64_
     // lanes per row: 4 for narrow aligned rows (8 float4 per lane at C = 128), 8 up to 256 columns, a whole warp above
     pl.lpr = (C <= 128 && pl.aligned && pl.tma) ? 4 : (C <= 256 ? 8 : 32);
     if (pl.tma) {
-        // rows per chunk: one sweep of the 16 warps when it fits (<= 64 KB per stage), else fewer rows
-        int R = kRecWarps * (32 / pl.lpr);                       // 128, 64 or 16
-        while (R > 8 && (size_t)R * row_bytes > 65536) R >>= 1;
-        if ((size_t)R * row_bytes > 65536) pl.tma = false;
+        // rows per chunk: one sweep of the 8 warps when it fits (<= 32 KB per stage), else fewer rows
+        int R = kRecWarps * (32 / pl.lpr);                       // 64, 32 or 8
+        while (R > 8 && (size_t)R * row_bytes > 32768) R >>= 1;
+        if ((size_t)R * row_bytes > kRecStageBudget / 2) pl.tma = false;
         pl.R = R;
     }
     if (pl.tma) {
         const size_t per_stage = (size_t)pl.R * row_bytes + (size_t)pl.R * sizeof(L);
-        int S = (int)((190 * 1024) / per_stage);
+        int S = (int)(kRecStageBudget / per_stage);
         pl.S = S > kMaxStages ? kMaxStages : S;
         if (pl.S < 2) pl.tma = false;
     }
@@ -790,7 +828,7 @@ static RecPlan plan_records(const float* scores, int64_t ld, const L* gt, int64_
         pl.smem = sizeof(RecShared) + 16;
     }
     const int64_t n_chunks = (N + pl.R - 1) / pl.R;
-    const int cap = pl.tma ? sm_count() : sm_count() * 2;
+    const int cap = sm_count() * kRecCtasPerSm;
     pl.grid = (int)(n_chunks < 1 ? 1 : (n_chunks > cap ? cap : n_chunks));
     return pl;
 }
@@ -804,7 +842,7 @@ static int launch_records_k(const RecPlan& pl, const float* scores, int64_t ld, 
         OSB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         smem_set = pl.smem;
     }
-    k<<<pl.grid, kRecThreads, pl.smem, st>>>(scores, ld, gt, N, C, pl.R, pl.S, unk_label, pl.vec4, recU, recK, totals);
+    k<<<pl.grid, kRecThreads, pl.smem, st>>>(scores, ld, gt, N, C, pl.R, pl.S, unk_label, pl.vec4, recU, recK, totals, g_rec_debug);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
@@ -904,6 +942,7 @@ using namespace osb;
 
 // developer hook (not part of the public header): device buffer of [grid][32] int64 SM clock stamps, or NULL
 extern "C" void osb_debug_set_curve_trace(void* p) { g_curve_trace = reinterpret_cast<long long*>(p); }
+extern "C" void osb_debug_set_records_mode(int m) { g_rec_debug = m; }
 
 // workspace of the composed entry: [totals 256 B][curve ws][rec_unk N][rec_known N].  Everything that must be zero
 // between calls (totals, barrier counters, digit histograms) sits at FIXED offsets at the front, so one workspace

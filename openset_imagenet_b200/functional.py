@@ -91,3 +91,37 @@ class HeadPlan:
         self.forward(x, w, y, bias)
         self.backward_dx(x, w, gscale)
         self.backward_dw(x, w, gscale)
+
+
+class OscrPlan:
+    """Buffers + launch arguments for OSCR over a fixed number of samples: ``run(scores, gt)`` enqueues the two
+    kernels (row reduce, cooperative sort + scan) with no allocation and no host synchronisation, so an
+    evaluation loop (or a CUDA graph) can replay it.  Outputs (device tensors, overwritten by every call):
+      taus [N] f32, ccr_cnt / fpr_cnt [N] i64, ccr / fpr [N] f64, meta [5] i64 =
+      (n_unique, n_known, n_correct, n_unk, n_bad); the reference's arrays are the first ``meta[0] - 1`` entries.
+    """
+
+    _LABELS = {torch.int64: L.LABEL_I64, torch.float32: L.LABEL_F32, torch.int32: L.LABEL_I32}
+
+    def __init__(self, N: int, C: int, unk_label: int = -1, device=None):
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.N, self.C, self.unk_label = int(N), int(C), int(unk_label)
+        d, cap = self.dev, max(int(N), 1)
+        self.taus = torch.empty(cap, dtype=torch.float32, device=d)
+        self.ccr_cnt = torch.empty(cap, dtype=torch.int64, device=d)
+        self.fpr_cnt = torch.empty(cap, dtype=torch.int64, device=d)
+        self.ccr = torch.empty(cap, dtype=torch.float64, device=d)
+        self.fpr = torch.empty(cap, dtype=torch.float64, device=d)
+        self.meta = torch.zeros(5, dtype=torch.int64, device=d)
+        self.ws = torch.zeros(L.size("osb_oscr_workspace_bytes", self.N) + 256, dtype=torch.uint8, device=d)
+        self.launches_per_call = 2
+
+    def run(self, scores: torch.Tensor, gt: torch.Tensor):
+        if scores.shape != (self.N, self.C) or scores.dtype != torch.float32 or scores.stride(1) != 1:
+            raise ValueError("scores must be a float32 [N, C] tensor with unit column stride")
+        if gt.shape != (self.N,) or gt.dtype not in self._LABELS or not gt.is_contiguous():
+            raise ValueError("gt must be a contiguous int64 / int32 / float32 [N] tensor")
+        L.call("osb_oscr", L.ptr(scores), scores.stride(0), L.ptr(gt), self._LABELS[gt.dtype], self.N, self.C, self.unk_label,
+               L.ptr(self.taus), L.ptr(self.ccr_cnt), L.ptr(self.fpr_cnt), L.ptr(self.ccr), L.ptr(self.fpr), L.ptr(self.meta),
+               L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+        return self

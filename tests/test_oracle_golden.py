@@ -193,3 +193,16 @@ def test_live_reference_oscr_and_confidence(seed):
     o = O.confidence(s, gt, 0.1, -1)
     assert (o[1], o[3]) == (r[1], r[3])
     assert o[0] == pytest.approx(r[0], rel=2e-6) and o[2] == pytest.approx(r[2], rel=2e-6)
+
+
+def test_synthetic_generators_of_the_product_match_the_oracle_copies():
+    """bench.py draws its inputs from openset_imagenet_b200.synth (the product may not import the oracle);
+    both generators must stay identical so that parity checks see the same data."""
+    from openset_imagenet_b200 import synth
+    np.testing.assert_array_equal(synth.make_labels(500, 116, 1 / 3, seed=3), O.make_labels(500, 116, 1 / 3, seed=3))
+    g1, s1 = synth.make_oscr_case(2000, 31, seed=4)
+    g2, s2 = O.make_oscr_case(2000, 31, seed=4)
+    np.testing.assert_array_equal(g1, g2)
+    np.testing.assert_array_equal(s1, s2)
+    y = synth.make_labels(4000, 20, 0.3, seed=5, neg_label=19)
+    np.testing.assert_array_equal(synth.class_weights_from_labels(y, 20), O.class_weights_from_labels(y, 20))

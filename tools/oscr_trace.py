@@ -36,4 +36,7 @@ for k, nm in [(24, "scan start"), (25, "scan tile"), (26, "barrier"), (27, "emit
     d = cur - prev
     print(f"scan   {nm:14s} med {np.median(d):8.0f} max {d.max():8.0f} min {d.min():8.0f}")
     prev = cur
+b = t[:, 6]
+for k, nm in [(28, "p1 zeroed"), (29, "p1 round 0 done"), (30, "p1 rounds done"), (31, "p1 block sync")]:
+    print(f"pass 1 detail {nm:16s} med {np.median(t[:, k] - b):8.0f} (since pass start)")
 print("total cycles (median CTA):", np.median(t[:, 27] - t[:, 0]))
