@@ -124,35 +124,35 @@ def make_head_inputs(cfg, dev, nbuf, seed):
 # ------------------------------------------------------------------------------------------------
 def run_head(args, cfg, rank, world, dev, peaks):
     import torch.distributed as dist
-    from openset_imagenet_b200.functional import HeadPlan
+    from openset_imagenet_b200.dist import ShardedHeadPlan
 
     B, K, C = cfg["B"], cfg["K"], cfg["C"]
     nbuf = 3                                        # 3 x 64 MB of features + 64 MB dX + 32 MB dZ: far larger than the 126 MB L2
     xs, ys, ys_np, w, cw = make_head_inputs(cfg, dev, nbuf, seed=1234 + rank)
-    plan = HeadPlan(B, K, C, cfg["variant"], class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None,
-                    device=dev)
-    den_hook = None
-    flat = torch.empty(C * K + 2, dtype=torch.float32, device=dev)
-    if world > 1:
-        def den_hook(den):                          # global mean: the denominator is summed over the shards
-            dist.all_reduce(den, op=dist.ReduceOp.SUM)
+    sp = ShardedHeadPlan(B, K, C, cfg["variant"], class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None,
+                         device=dev)
+    plan = sp.plan
 
     def step(i, ev=None):
+        """label stats -> fused forward -> dW -> [all-reduce of dW|loss  overlapped with  dX]"""
         x, y = xs[i % nbuf], ys[i % nbuf]
-        plan.label_stats(y, den_hook)
-        if ev: ev[0].record()
+        if ev is None:
+            sp.finish(sp.step(x, w, y))
+            return
+        plan.label_stats(y, sp._den_hook)
+        ev[0].record()
         plan.forward(x, w, y)
-        if ev: ev[1].record()
+        ev[1].record()
         plan.backward_dw(x, w)
-        if ev: ev[2].record()
-        if world > 1:                               # dW first so its all-reduce can overlap the dX GEMM
-            flat[:C * K].copy_(plan.dw.view(-1))
-            flat[C * K] = plan.loss[0]
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-        plan.backward_dx(x, w)
-        if ev: ev[3].record()
+        ev[2].record()
+        work = dist.all_reduce(sp.flat, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
         if world > 1:
-            work.wait()
+            sp._L.load().osb_set_cta_limit(sp._sms - sp.sm_reserve)
+        plan.backward_dx(x, w)
+        if world > 1:
+            sp._L.load().osb_set_cta_limit(0)
+        ev[3].record()
+        sp.finish(work)
 
     for i in range(args.warmup):
         step(i)
@@ -160,21 +160,17 @@ def run_head(args, cfg, rank, world, dev, peaks):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index) as clk:
         t0.record()
         for i in range(args.steps):
-            step(i, evs[i])
+            step(i)
         t1.record()
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1)
-    k_fwd = statistics.mean(e[0].elapsed_time(e[1]) for e in evs) * 1e3
-    k_dw = statistics.mean(e[1].elapsed_time(e[2]) for e in evs) * 1e3
-    k_dx = statistics.mean(e[2].elapsed_time(e[3]) for e in evs) * 1e3
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -182,6 +178,16 @@ def run_head(args, cfg, rank, world, dev, peaks):
     loss_val = float(plan.loss.item())
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+
+    # per-kernel times: a second, shorter loop with events between the launches (kept out of the headline loop)
+    n_ev = max(10, min(args.steps, 100))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
+    for i in range(n_ev):
+        step(i, evs[i])
+    torch.cuda.synchronize()
+    k_fwd = statistics.mean(e[0].elapsed_time(e[1]) for e in evs) * 1e3
+    k_dw = statistics.mean(e[1].elapsed_time(e[2]) for e in evs) * 1e3
+    k_dx = statistics.mean(e[2].elapsed_time(e[3]) for e in evs) * 1e3
 
     gemm_flops = 2.0 * B * K * C
     kernels = {"head_fwd_kernel": k_fwd, "head_dw_kernel+dw_reduce_kernel": k_dw, "head_dx_kernel": k_dx}
@@ -200,34 +206,50 @@ def run_head(args, cfg, rank, world, dev, peaks):
     }
     roof["frac"] = roof["achieved"] / roof["peak"]
 
-    # ---- end to end from pinned host buffers through the C ABI ----
+    # ---- end to end from pinned host buffers through the C ABI: every step copies ITS features and labels host ->
+    # device and reads its loss back.  Two device input slots: the copy of step i+1 (copy stream) overlaps the kernels
+    # of step i, as a training loop with a prefetching loader does.
     e2e = None
     if not args.no_e2e:
         hx = [x.cpu().pin_memory() for x in xs[:2]]
         hy = [y.cpu().pin_memory() for y in ys[:2]]
-        dxh = torch.empty(B, K, dtype=torch.bfloat16).pin_memory()
-        dwh = torch.empty(C, K, dtype=torch.float32).pin_memory()
         lossh = torch.empty(1, dtype=torch.float32).pin_memory()
-        xd, yd = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+        xd = [torch.empty_like(xs[0]) for _ in range(2)]
+        yd = [torch.empty_like(ys[0]) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event() for _ in range(2)]       # slot filled
+        freed = [torch.cuda.Event() for _ in range(2)]       # slot consumed
         n_e2e = max(3, min(args.steps, 40))
 
-        def e2e_step(i):
-            xd.copy_(hx[i % 2], non_blocking=True)
-            yd.copy_(hy[i % 2], non_blocking=True)
-            plan.step(xd, w, yd, den_scale_hook=den_hook)
-            lossh.copy_(plan.loss, non_blocking=True)
-            dxh.copy_(plan.dx, non_blocking=True)
-            dwh.copy_(plan.dw, non_blocking=True)
+        def prefetch(i):
+            sl = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[sl])
+                xd[sl].copy_(hx[i % 2], non_blocking=True)
+                yd[sl].copy_(hy[i % 2], non_blocking=True)
+                ready[sl].record(copy_stream)
 
-        for i in range(3):
-            e2e_step(i)
+        def e2e_loop(n):
+            for sl in range(2):
+                freed[sl].record(main)
+            prefetch(0)
+            for i in range(n):
+                sl = i % 2
+                if i + 1 < n:
+                    prefetch(i + 1)
+                main.wait_event(ready[sl])
+                sp.finish(sp.step(xd[sl], w, yd[sl]))
+                freed[sl].record(main)
+                lossh.copy_(plan.loss, non_blocking=True)
+
+        e2e_loop(3)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(n_e2e):
-            e2e_step(i)
+        e2e_loop(n_e2e)
         b.record()
         torch.cuda.synchronize()
         ems = a.elapsed_time(b)
@@ -236,10 +258,12 @@ def run_head(args, cfg, rank, world, dev, peaks):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {"value": world * B * n_e2e / (ems * 1e-3), "unit": "samples/s", "steps": n_e2e,
-               "h2d_bytes_per_step": B * K * 2 + B * 8, "d2h_bytes_per_step": B * K * 2 + C * K * 4 + 4,
-               "ms_per_step": ems / n_e2e}
+               "h2d_bytes_per_step": B * K * 2 + B * 8, "d2h_bytes_per_step": 4,
+               "ms_per_step": ems / n_e2e,
+               "note": "features+labels copied from pinned host memory every step (prefetched one step ahead on a copy stream), "
+                       "loss read back every step; dX and dW stay on the device for the backbone / optimiser"}
     return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clk.summary(), loss=loss_val,
-                launches=plan.launches_per_step * args.steps)
+                launches=sp.launches_per_step * args.steps)
 
 
 def run_oscr(args, rank, world, dev, peaks):
@@ -300,6 +324,14 @@ def run_oscr(args, rank, world, dev, peaks):
                         "peak_kind": f"{peaks['src']} copy bandwidth", "algorithmic_bytes": alg_bytes, "traffic": None,
                         "kernels": "oscr_records_kernel (one pass over the scores) + oscr_curve_kernel (sort + scan, L2 resident)"}}
     out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
+    if rank == 0 and world > 1:
+        # the sharded result must be bit-identical to the single-GPU one over the whole evaluation set
+        ref = OscrPlan(N, C, -1, device=dev).run(torch.tensor(s_np, device=dev), torch.tensor(gt_np, device=dev))
+        nu = int(ref.meta[0].item())
+        same = (int(r[5][0].item()) == nu and torch.equal(r[2][:nu], ref.ccr_cnt[:nu]) and torch.equal(r[3][:nu], ref.fpr_cnt[:nu])
+                and torch.equal(r[4][:nu], ref.taus[:nu]) and torch.equal(r[0][:nu], ref.ccr[:nu])
+                and torch.equal(r[1][:nu].nan_to_num(-1.0), ref.fpr[:nu].nan_to_num(-1.0)))
+        out["parity"] = {"sharded_bit_identical_to_single_gpu": bool(same)}
     if rank == 0 and world == 1 and not args.no_e2e:
         import openset_imagenet_b200 as osb
         from oracle import oracle as O
@@ -394,6 +426,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     import openset_imagenet_b200  # noqa: F401  (loads libosb.so; raises if missing)
 
@@ -424,7 +458,7 @@ def main():
                                                   "port -> backward -> softmax -> confidence port (oracle/ref_port.py)"}
             if oscr is not None:
                 line["oscr"] = oscr
-            print(json.dumps(line))
+            print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -28,6 +28,7 @@ SIGNATURES = {
     "osb_last_error": (C.c_char_p, []),
     "osb_device_check": (_i, []),
     "osb_sm_count": (_i, []),
+    "osb_set_cta_limit": (_i, [_i]),
     "osb_label_stats": (_i, [_p, _p, _i64, _i, _i, _i64, _p, _p, _p, _sz, _p]),
     "osb_loss_workspace_bytes": (_sz, [_i64]),
     "osb_loss_from_logits": (_i, [_p, _i, _i64, _p, _p, _i64, _i, _i, _d, _i64, _p, _i,

@@ -897,7 +897,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         rc = set_smem(head_dx_kernel, kDxSmemBytes);
         if (rc) return rc;
         const int total = (int)((B + BM - 1) / BM) * ((K + kDxBN - 1) / kDxBN);
-        int grid = sm_count();
+        int grid = cta_limit();
         if (grid > total) grid = total;
         head_dx_kernel<<<grid, kThreads, kDxSmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
         OSB_LAUNCH_CHECK();

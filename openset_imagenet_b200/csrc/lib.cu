@@ -48,6 +48,12 @@ int check_device() {
     return probe(dev);
 }
 
+static int g_cta_limit = 0;
+int cta_limit() {
+    const int sms = sm_count();
+    return (g_cta_limit > 0 && g_cta_limit < sms) ? g_cta_limit : sms;
+}
+
 int sm_count() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
@@ -61,3 +67,8 @@ extern "C" int osb_abi_version(void) { return OSB_ABI_VERSION; }
 extern "C" const char* osb_last_error(void) { return osb::g_err; }
 extern "C" int osb_device_check(void) { return osb::check_device(); }
 extern "C" int osb_sm_count(void) { return osb::sm_count(); }
+extern "C" int osb_set_cta_limit(int max_ctas) {
+    const int old = osb::g_cta_limit;
+    osb::g_cta_limit = max_ctas < 0 ? 0 : max_ctas;
+    return old;
+}

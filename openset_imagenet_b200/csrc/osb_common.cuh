@@ -19,6 +19,7 @@ namespace osb {
 void set_error(const char* fmt, ...);
 int  check_device();                 // OSB_OK or OSB_ERR_ARCH (cached per device)
 int  sm_count();                     // cached
+int  cta_limit();                    // sm_count() or the smaller bound set by osb_set_cta_limit()
 
 #define OSB_REQUIRE(cond, code, ...)                 \
     do {                                             \

@@ -94,6 +94,65 @@ class ShardedHead:
         return work, unpack
 
 
+class ShardedHeadPlan:
+    """Allocation-free batch-sharded head step (``functional.HeadPlan`` per rank + ONE all-reduce).
+
+    The kernels write dW, db and this shard's loss contribution straight into one packed float32 buffer
+    ``flat = [dW | db | loss]``; after the dW GEMM that buffer is all-reduced asynchronously while the dX GEMM
+    (local, needs no communication) runs on ``SMs - sm_reserve`` CTAs so that the collective finds free SMs.
+    Denominator of the global mean: the entropic loss counts every row, so with equal shards it is
+    ``B_local * world`` and needs no communication; the softmax / garbage variants all-reduce one double before
+    the forward kernel.
+    """
+
+    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=16, device=None, **plan_kwargs):
+        from . import _lib as L
+        from .functional import HeadPlan
+        self.group = group
+        self.rank, self.world = world()
+        self.variant = variant
+        bias = bool(plan_kwargs.get("bias", False))
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.flat = torch.zeros(C * K + (C if bias else 0) + 1, dtype=torch.float32, device=dev)
+        self.plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=self.flat, **plan_kwargs)
+        self._L = L
+        self._sms = L.size("osb_sm_count")
+        self.sm_reserve = int(sm_reserve) if self.world > 1 else 0
+        self.launches_per_step = self.plan.launches_per_step      # our kernels only (the collective is NCCL's)
+
+    def _den_hook(self, den):
+        if self.world == 1:
+            return
+        if self.variant == "entropic":
+            den.mul_(self.world)                     # every row counts and shards are equal: no communication
+        else:
+            dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, x, w, y, bias=None):
+        """Returns the async work handle of the gradient all-reduce (None on one GPU); ``finish(work)`` makes the
+        current stream wait for it.  After that ``plan.dw`` / ``plan.db`` hold the full-batch gradients and
+        ``plan.loss`` the full-batch loss on every rank; ``plan.dx`` is this shard's d loss / d features."""
+        p = self.plan
+        p.label_stats(y, self._den_hook)
+        p.forward(x, w, y, bias)
+        p.backward_dw(x, w)
+        work = None
+        if self.world > 1:
+            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._L.load().osb_set_cta_limit(self._sms - self.sm_reserve)
+        try:
+            p.backward_dx(x, w)
+        finally:
+            if self.world > 1:
+                self._L.load().osb_set_cta_limit(0)
+        return work
+
+    @staticmethod
+    def finish(work):
+        if work is not None:
+            work.wait()
+
+
 # ------------------------------------------------------------------------------------------------
 # OSCR
 # ------------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ class HeadPlan:
 
     def __init__(self, B: int, K: int, C: int, variant: str = "entropic", unk_weight: float = 1.0,
                  class_weights: torch.Tensor | None = None, ignore_index: int | None = None,
-                 last_valid_class=None, bias: bool = False, device=None):
+                 last_valid_class=None, bias: bool = False, device=None, grad_buffer: torch.Tensor | None = None):
         if K % 64 != 0:
             raise ValueError("HeadPlan needs in_features % 64 == 0 (FusedOpenSetHead pads other widths)")
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -41,15 +41,23 @@ class HeadPlan:
                               dtype=torch.uint8, device=d)
         self.den = torch.empty(1, dtype=torch.float64, device=d)
         self.label_counts = torch.empty(4, dtype=torch.int64, device=d)
-        self.loss = torch.empty(1, dtype=torch.float32, device=d)
+        # [dW | db | loss] may live in one caller-owned float32 buffer (the packed all-reduce buffer of dist.py), so
+        # that the kernels write straight into it and no gather copy is needed
+        n_flat = C * K + (C if bias else 0) + 1
+        if grad_buffer is None:
+            grad_buffer = torch.empty(n_flat, dtype=torch.float32, device=d)
+        if grad_buffer.dtype != torch.float32 or grad_buffer.numel() < n_flat or not grad_buffer.is_contiguous():
+            raise ValueError(f"grad_buffer must be a contiguous float32 tensor with at least {n_flat} elements")
+        self.flat = grad_buffer[:n_flat]
+        self.loss = self.flat[n_flat - 1:]
         self.loss_num = torch.empty(1, dtype=torch.float64, device=d)
         self.stats = torch.empty(3, B, dtype=torch.float32, device=d)
         self.p_target, self.p_max, self.p_max_all = self.stats[0], self.stats[1], self.stats[2]
         self.pred = torch.empty(B, dtype=torch.int32, device=d)
         self.dz = torch.empty(B, self.lddz, dtype=torch.bfloat16, device=d)
         self.dx = torch.empty(B, K, dtype=torch.bfloat16, device=d)
-        self.dw = torch.empty(C, K, dtype=torch.float32, device=d)
-        self.db = torch.empty(C, dtype=torch.float32, device=d) if bias else None
+        self.dw = self.flat[:C * K].view(C, K)
+        self.db = self.flat[C * K:C * K + C] if bias else None
         self.launches_per_step = 5 + (1 if bias else 0)   # label_stats, fwd, dx, dw, dw-reduce (+ db)
 
     def _check(self, x, w, y):
