@@ -47,6 +47,15 @@ def load_peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
 
 
+def load_traffic():
+    """DRAM bytes per launch from the committed ncu --set full captures (profiles/traffic.json), or {}."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return {k: v for k, v in json.load(open(p)).items() if not k.startswith("_")}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """Polls SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -197,7 +206,8 @@ def run_head(args, cfg, rank, world, dev, peaks):
         "bound": "tensor", "kernel": dom, "unit": "TFLOP/s",
         "achieved": gemm_flops / kernels[dom] / 1e6, "peak": peaks["tc_sustained"],
         "peak_kind": f"{peaks['src']} cuBLAS bf16 sustained (kernels timed inside a long step); burst is {peaks['tc_burst']}",
-        "traffic": None,
+        "traffic": (load_traffic().get(dom, {}).get("bytes") if (B, K, C) == (16384, 2048, 1000) else None),
+        "traffic_note": "dram read+write bytes of one launch from the committed ncu --set full capture (profiles/traffic.json)",
         "kernels_us": {k: round(v, 2) for k, v in kernels.items()},
         "kernels_tflops": {k: round(gemm_flops / v / 1e6, 1) for k, v in kernels.items()},
         "step": {"flops": 3 * gemm_flops, "us": round(step_us, 2), "achieved": 3 * gemm_flops / step_us / 1e6,
@@ -321,7 +331,10 @@ def run_oscr(args, rank, world, dev, peaks):
                       "rows_per_gpu": n_loc, "n_thresholds": n_thr,
                       "l2": "two alternating score buffers, each larger than L2; no flush writes"},
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                        "peak_kind": f"{peaks['src']} copy bandwidth", "algorithmic_bytes": alg_bytes, "traffic": None,
+                        "peak_kind": f"{peaks['src']} copy bandwidth", "algorithmic_bytes": alg_bytes,
+                        "traffic": (sum(load_traffic().get(k, {}).get("bytes", 0) for k in ("oscr_records_kernel", "oscr_curve_kernel")) or None)
+                        if (world == 1 and N == 1_000_000 and C == 116) else None,
+                        "traffic_note": "dram read+write bytes of both launches from the committed ncu --set full capture (profiles/traffic.json)",
                         "kernels": "oscr_records_kernel (one pass over the scores) + oscr_curve_kernel (sort + scan, L2 resident)"}}
     out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
     if rank == 0 and world > 1:

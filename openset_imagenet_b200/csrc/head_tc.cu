@@ -750,9 +750,14 @@ static int dw_splits(int B, int K, int C) {
     return s;
 }
 
+// once per kernel (per process): the attribute is sticky
 template <typename KernelT>
 static int set_smem(KernelT kernel, int bytes) {
+    static bool done = false;          // one instance per KernelT instantiation... and per kernel pointer below
+    static const void* last = nullptr;
+    if (done && last == reinterpret_cast<const void*>(kernel)) return OSB_OK;
     OSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done = true; last = reinterpret_cast<const void*>(kernel);
     return OSB_OK;
 }
 

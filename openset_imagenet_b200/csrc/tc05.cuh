@@ -199,9 +199,20 @@ static inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = 64 columns x box_rows rows, SWIZZLE_128B,
-// out-of-bounds elements read as zero.  Returns 0 on success.
+// out-of-bounds elements read as zero.  Returns 0 on success.  Encoding costs ~1-2 us of host time, which is
+// what bounds the small-batch configurations, so the last few descriptors are kept in a thread-local cache
+// (a descriptor depends only on the arguments below).
 static inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                                  uint32_t box_rows, uint32_t box_cols = 64) {
+    struct Entry { const void* base; uint64_t rows, cols, ld; uint32_t box_rows, box_cols; bool valid; CUtensorMap map; };
+    constexpr int kSlots = 32;
+    static thread_local Entry cache[kSlots];
+    const uint64_t h = (reinterpret_cast<uint64_t>(base) >> 8) ^ (rows * 0x9E3779B97F4A7C15ull) ^ (cols << 20) ^ (ld << 40) ^ box_rows;
+    Entry& e = cache[(h ^ (h >> 17) ^ (h >> 31)) % kSlots];
+    if (e.valid && e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.box_rows == box_rows && e.box_cols == box_cols) {
+        *out = e.map;
+        return 0;
+    }
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return -1;
     cuuint64_t dims[2] = {cols, rows};
@@ -211,7 +222,9 @@ static inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t ro
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)r;
+    if (r != CUDA_SUCCESS) return (int)r;
+    e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.box_rows = box_rows; e.box_cols = box_cols; e.map = *out; e.valid = true;
+    return 0;
 }
 
 }  // namespace osb

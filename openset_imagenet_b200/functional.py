@@ -91,6 +91,22 @@ class HeadPlan:
                L.ptr(gscale), None, self.K, L.ptr(self.dw), L.ptr(self.db), L.ptr(self.ws), self.ws.numel(),
                L.stream_ptr(self.dev))
 
+    def capture(self, x, w, y, bias=None, gscale=None):
+        """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five
+        kernels on the CURRENT CONTENTS of those tensors with a single launch call.  The small-batch configurations
+        (B <= 1024) are bound by launch latency, not by the kernels, so this is the path to use in a training loop."""
+        self._check(x, w, y)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.step(x, w, y, bias, gscale)                 # warm-up outside capture (function attributes, descriptors)
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.step(x, w, y, bias, gscale)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        return graph
+
     def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False):
         """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches."""
         if check:

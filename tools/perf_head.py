@@ -51,6 +51,13 @@ def head_case(B, K, C, variant="entropic"):
         med, mn = timeit(fn)
         med2, mn2 = timeit(fn, flush_l2=False)
         print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | warm med {med2:9.1f} us" + (f" | {f/med/1e6:8.1f} TF/s cold, {f/med2/1e6:8.1f} warm" if f else ""))
+    # whole step through HeadPlan: eager (5 launches) and replayed from a CUDA graph
+    from openset_imagenet_b200.functional import HeadPlan
+    plan = HeadPlan(B, K, C, variant, class_weights=cw, last_valid_class=-1 if variant == "garbage" else None, device=dev)
+    graph = plan.capture(x, w, y)
+    for name, fn in [("plan.step eager", lambda: plan.step(x, w, y)), ("plan graph", graph.replay)]:
+        med, mn = timeit(fn); med2, mn2 = timeit(fn, flush_l2=False)
+        print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | warm med {med2:9.1f} us | {3*fl/med/1e6:8.1f} TF/s cold")
     # cuBLAS reference points for the same three GEMMs
     xf, wf, dzf = x, w, dz[:, :C].contiguous()
     for name, fn in [("cublas X@W^T", lambda: xf @ wf.t()), ("cublas dZ@W", lambda: dzf @ wf), ("cublas dZ^T@X", lambda: dzf.t() @ xf)]:
