@@ -140,6 +140,14 @@ int osb_confidence(const float* scores, int64_t ld, const int64_t* y, int64_t N,
                    float one_plus_offset, int64_t unknown_class, int valid_cols,
                    double* sums, int64_t* counts, void* ws, size_t ws_bytes, void* stream);
 
+/* Streaming variant for the validation loop (train.py:172-192): the rows of one batch already reduced by the
+ * fused head to p_target[i] = s[i, y_i] and p_max[i] = max_c s[i, :valid_cols] (osb_head_forward row_ptgt /
+ * row_pmax), so no [N, C] score tensor exists.  accumulate != 0 adds this batch to sums[2] / counts[3]
+ * (same meaning as above), accumulate == 0 overwrites them.  One block, fixed summation order. */
+int osb_confidence_from_stats(const float* p_target, const float* p_max, const int64_t* y, int64_t N, int C,
+                              float one_plus_offset, int64_t unknown_class, int accumulate,
+                              double* sums, int64_t* counts, void* stream);
+
 /* ---- OSCR (util.py:90-122) ----------------------------------------------------------------- *
  * RECORD = (uint64) key << 32 | type.  key = order-preserving uint32 image of a float32 score
  * (-0.0 == +0.0); type 0 = known row, arg-max != label; 1 = known row, arg-max == label (util.py:114);

@@ -5,10 +5,10 @@ softmax / garbage-class cross-entropy variants, ``metrics.confidence``, ``util.c
 CCR@FPR lookup, plus ``model.FusedOpenSetHead`` (tcgen05/TMEM linear + loss + backward).  Everything
 computes in hand-written CUDA kernels behind the C ABI of ``include/osb.h``; there is no CPU fallback.
 """
-from . import losses, metrics, util  # noqa: F401
+from . import losses, metrics, train, util  # noqa: F401
 from .losses import CrossEntropyLoss, EntropicOpensetLoss, make_loss  # noqa: F401
-from .metrics import confidence  # noqa: F401
+from .metrics import StreamingConfidence, confidence  # noqa: F401
 from .util import calculate_oscr, ccr_at_fpr  # noqa: F401
 
-__all__ = ["losses", "metrics", "util", "EntropicOpensetLoss", "CrossEntropyLoss", "make_loss",
+__all__ = ["losses", "metrics", "train", "util", "StreamingConfidence", "EntropicOpensetLoss", "CrossEntropyLoss", "make_loss",
            "confidence", "calculate_oscr", "ccr_at_fpr"]

@@ -39,6 +39,7 @@ SIGNATURES = {
     "osb_head_backward": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "osb_confidence_workspace_bytes": (_sz, [_i64]),
     "osb_confidence": (_i, [_p, _i64, _p, _i64, _i, _f, _i64, _i, _p, _p, _p, _sz, _p]),
+    "osb_confidence_from_stats": (_i, [_p, _p, _p, _i64, _i, _f, _i64, _i, _p, _p, _p]),
     "osb_oscr_workspace_bytes": (_sz, [_i64]),
     "osb_oscr_curve_workspace_bytes": (_sz, [_i64]),
     "osb_oscr_records": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _p, _p, _p, _p]),

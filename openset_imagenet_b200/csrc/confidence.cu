@@ -191,6 +191,46 @@ static int launch_conf_bulk(const StreamPlan& pl, const float* scores, const int
     return OSB_OK;
 }
 
+
+// ---- streaming variant: per-row statistics of the fused head instead of a score matrix ----------
+// One block, fixed summation order; adds one validation batch to the running totals (train.py:172-192 without
+// the all_scores tensor).
+__global__ void __launch_bounds__(1024)
+confidence_from_stats_kernel(const float* __restrict__ p_target, const float* __restrict__ p_max, const int64_t* __restrict__ y,
+                             int64_t N, int C, float one_plus_offset, int64_t unknown_class, int accumulate,
+                             double* __restrict__ sums, int64_t* __restrict__ counts) {
+    double kn_sum = 0.0, neg_sum = 0.0;
+    long long kn_cnt = 0, neg_cnt = 0, bad_cnt = 0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const int64_t lab = y[i];
+        const bool unknown = lab == unknown_class;                           // metrics.py:25
+        const bool known = lab >= 0 && !unknown;                             // metrics.py:26
+        const bool bad = known && lab >= C;
+        if (known && !bad) kn_sum += (double)p_target[i];                    // metrics.py:33
+        if (unknown) neg_sum += (double)(one_plus_offset - p_max[i]);        // metrics.py:36-40
+        kn_cnt += known; neg_cnt += unknown; bad_cnt += bad;
+    }
+    __shared__ double sh[5][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[5] = {kn_sum, neg_sum, (double)kn_cnt, (double)neg_cnt, (double)bad_cnt};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        v[q] = warp_sum(v[q]);
+        if (lane == 0) sh[q][warp] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[5] = {0, 0, 0, 0, 0};
+        for (int q = 0; q < 5; ++q)
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot[q] += sh[q][w];
+        sums[0] = (accumulate ? sums[0] : 0.0) + tot[0];
+        sums[1] = (accumulate ? sums[1] : 0.0) + tot[1];
+        counts[0] = (accumulate ? counts[0] : 0) + (int64_t)tot[2];
+        counts[1] = (accumulate ? counts[1] : 0) + (int64_t)tot[3];
+        counts[2] = (accumulate ? counts[2] : 0) + (int64_t)tot[4];
+    }
+}
+
 }  // namespace osb
 
 using namespace osb;
@@ -237,6 +277,18 @@ extern "C" int osb_confidence(const float* scores, int64_t ld, const int64_t* y,
     else
         confidence_kernel<32><<<grid, kConfThreads, 0, st>>>(scores, ld, y, N, C, one_plus_offset, unknown_class,
                                                              valid_cols, vec4, sums, counts, partials, ticket);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+extern "C" int osb_confidence_from_stats(const float* p_target, const float* p_max, const int64_t* y, int64_t N, int C,
+                                         float one_plus_offset, int64_t unknown_class, int accumulate,
+                                         double* sums, int64_t* counts, void* stream) {
+    OSB_ENTRY_GUARD();
+    OSB_REQUIRE(sums && counts && ((p_target && p_max && y) || N == 0), OSB_ERR_ARG, "osb_confidence_from_stats: null pointer");
+    OSB_REQUIRE(N >= 0 && C > 0, OSB_ERR_ARG, "osb_confidence_from_stats: bad sizes N=%lld C=%d", (long long)N, C);
+    confidence_from_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p_target, p_max, y, N, C, one_plus_offset, unknown_class,
+                                                                      accumulate, sums, counts);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }

@@ -45,6 +45,14 @@ int check_device() {
         set_error("no usable CUDA device (%s); libosb has no CPU fallback", cudaGetErrorName(e));
         return OSB_ERR_ARCH;
     }
+    // Bind the device's primary context to THIS thread once: driver entry points called without any runtime call
+    // before them (cuTensorMapEncodeTiled from an autograd worker thread whose allocations all came from PyTorch's
+    // cache) otherwise fail with CUDA_ERROR_INVALID_CONTEXT.
+    static thread_local int bound_dev = -1;
+    if (bound_dev != dev) {
+        cudaFree(nullptr);
+        bound_dev = dev;
+    }
     return probe(dev);
 }
 

@@ -67,3 +67,45 @@ def confidence(scores, target_labels, offset=0., unknown_class=-1, last_valid_cl
     kn_conf = s[0] / kn_count if kn_count else 0.0
     neg_conf = s[1] / neg_count if neg_count else 0.0
     return kn_conf, kn_count, neg_conf, neg_count
+
+
+class StreamingConfidence:
+    """Confidence of a whole validation set accumulated batch by batch from the fused head's per-row statistics
+    (``model.HeadStats``: ``p_target``, ``p_max``), so the ``all_scores [N_val, C]`` tensor of the reference's
+    ``validate`` (train.py:170,185) never exists.  No host synchronisation until ``result()``.
+
+    ``offset`` / ``unknown_class`` as in ``confidence``; the slice ``last_valid_class`` is a property of the head
+    (``FusedOpenSetHead(last_valid_class=...)``), which already applied it when it reduced ``p_max``.
+    """
+
+    def __init__(self, num_classes: int, offset=0., unknown_class=-1, device=None):
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.C = int(num_classes)
+        self.unknown_class = int(unknown_class)
+        self.one_plus_offset = float(torch.tensor(1.0 + offset, dtype=torch.float32))
+        self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.counts = torch.zeros(3, dtype=torch.int64, device=self.dev)
+
+    def reset(self):
+        self.sums.zero_()
+        self.counts.zero_()
+
+    def update(self, p_target: torch.Tensor, p_max: torch.Tensor, target_labels: torch.Tensor):
+        L.require_cuda(p_target, p_max, target_labels)
+        y = target_labels if target_labels.dtype == torch.int64 else target_labels.long()
+        y = y.contiguous()
+        n = y.shape[0]
+        if p_target.shape != (n,) or p_max.shape != (n,):
+            raise ValueError("p_target, p_max and target_labels must all be [batch]")
+        with torch.cuda.device(self.dev):
+            L.call("osb_confidence_from_stats", L.ptr(p_target.float().contiguous()), L.ptr(p_max.float().contiguous()), L.ptr(y),
+                   n, self.C, self.one_plus_offset, self.unknown_class, 1, L.ptr(self.sums), L.ptr(self.counts),
+                   L.stream_ptr(self.dev))
+
+    def result(self):
+        """``(kn_conf, kn_count, neg_conf, neg_count)`` with the reference's types and empty-group rule."""
+        s = self.sums.tolist()
+        kn_count, neg_count, bad = self.counts.tolist()
+        if bad:
+            raise IndexError(f"{bad} known label(s) out of range for {self.C} classes")
+        return (s[0] / kn_count if kn_count else 0.0), kn_count, (s[1] / neg_count if neg_count else 0.0), neg_count
