@@ -138,8 +138,19 @@ def run_head(args, cfg, rank, world, dev, peaks):
     B, K, C = cfg["B"], cfg["K"], cfg["C"]
     nbuf = 3                                        # 3 x 64 MB of features + 64 MB dX + 32 MB dZ: far larger than the 126 MB L2
     xs, ys, ys_np, w, cw = make_head_inputs(cfg, dev, nbuf, seed=1234 + rank)
-    sp = ShardedHeadPlan(B, K, C, cfg["variant"], class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None,
-                         device=dev)
+    plan_kw = dict(class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None, device=dev)
+    allreduce = "none"
+    if world > 1:
+        try:            # dW all-reduce over NVLink peer memory, fused with the split-K reduction (no NCCL on the data path)
+            sp = ShardedHeadPlan(B, K, C, cfg["variant"], peer_allreduce=True, sm_reserve=32, **plan_kw)
+            allreduce = "peer-memory kernel fused with the split-K reduction (osb_head_dw_allreduce), overlapped with dX"
+        except Exception as e:                                  # no symmetric memory on this box: NCCL all-reduce
+            if rank == 0:
+                print(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            sp = ShardedHeadPlan(B, K, C, cfg["variant"], sm_reserve=32, **plan_kw)
+            allreduce = "NCCL all-reduce of the packed fp32 [dW | loss] buffer, overlapped with dX"
+    else:
+        sp = ShardedHeadPlan(B, K, C, cfg["variant"], **plan_kw)
     plan = sp.plan
 
     def step(i, ev=None):
@@ -152,9 +163,14 @@ def run_head(args, cfg, rank, world, dev, peaks):
         ev[0].record()
         plan.forward(x, w, y)
         ev[1].record()
-        plan.backward_dw(x, w)
-        ev[2].record()
-        work = dist.all_reduce(sp.flat, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
+        if sp.peer is not None:
+            plan.backward_dw_partials(x)
+            ev[2].record()
+            work = sp.peer.run()
+        else:
+            plan.backward_dw(x, w)
+            ev[2].record()
+            work = dist.all_reduce(sp.flat, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
         if world > 1:
             sp._L.load().osb_set_cta_limit(sp._sms - sp.sm_reserve)
         plan.backward_dx(x, w)
@@ -184,7 +200,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    loss_val = float(plan.loss.item())
+    loss_val = float(sp.full_loss().item())
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -273,7 +289,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
                "note": "features+labels copied from pinned host memory every step (prefetched one step ahead on a copy stream), "
                        "loss read back every step; dX and dW stay on the device for the backbone / optimiser"}
     return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clk.summary(), loss=loss_val,
-                launches=sp.launches_per_step * args.steps)
+                launches=(sp.launches_per_step + (0 if sp.peer is None else 0)) * args.steps, allreduce=allreduce)
 
 
 def run_oscr(args, rank, world, dev, peaks):
@@ -374,6 +390,56 @@ def run_oscr(args, rank, world, dev, peaks):
     return out
 
 
+def run_resnet(args, rank, world, dev):
+    """BASELINE.json cfg 2: ResNet-50 (torchvision / cuDNN, bf16 autocast, channels_last) + fused entropic head,
+    Protocol-1 shape (116 classes), B = 256 synthetic 224x224 images per GPU; whole training step and the head's share."""
+    import openset_imagenet_b200 as osb
+    from openset_imagenet_b200 import synth
+    from openset_imagenet_b200.model import ResNet50
+    B, C = 256, 116
+    torch.manual_seed(0)
+    model = ResNet50(fc_layer_dim=C, out_features=C, logit_bias=False, variant="entropic").to(dev).to(memory_format=torch.channels_last)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+    imgs = [torch.randn(B, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last) for _ in range(2)]
+    ys = [torch.tensor(synth.make_labels(B, C, 1 / 3, seed=i), device=dev) for i in range(2)]
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            j, _ = model.forward_loss(imgs[i % 2], ys[i % 2])
+        j.backward()
+        opt.step()
+        return j
+
+    steps, warm = min(args.steps, 30), max(3, min(args.warmup, 5))
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        j = step(i)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    # the head alone on the same shapes (features [B, 116] bf16 -> 116 classes), forward + backward
+    feats = torch.randn(B, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    for _ in range(3):
+        model.logits.loss(feats, ys[0]).backward()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(20):
+        model.logits.loss(feats, ys[0]).backward()
+    b.record()
+    torch.cuda.synchronize()
+    head_us = a.elapsed_time(b) / 20 * 1e3
+    return {"metric": "ResNet-50 + EOS training step samples/s", "value": world * B / (ms * 1e-3), "unit": "samples/s",
+            "ms_per_step": ms, "steps": steps, "warmup": warm, "head_fwd_bwd_us": head_us, "head_share": head_us * 1e-3 / ms,
+            "loss": float(j.item()),
+            "config": {"workload": "ResNet-50 + fused entropic head, Protocol 1 shape (116 classes), B=256 synthetic 224x224 images, "
+                                   "bf16 autocast, channels_last, SGD momentum", "global_batch": B * world}}
+
+
 def head_cpu_baseline(cfg, sample_rows, iters):
     """The reference path op for op on the host cores (oracle/ref_port.py), on `sample_rows` rows of the workload."""
     from openset_imagenet_b200 import synth as O
@@ -399,7 +465,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="head", choices=["head", "bg", "oscr"])
+    ap.add_argument("--workload", default="head", choices=["head", "bg", "oscr", "resnet"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-oscr", action="store_true")
     args = ap.parse_args()
@@ -444,7 +510,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import openset_imagenet_b200  # noqa: F401  (loads libosb.so; raises if missing)
 
-    if args.workload == "oscr":
+    if args.workload == "resnet":
+        o = run_resnet(args, rank, world, dev)
+        if rank == 0:
+            o.update({"n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
+            print(json.dumps(o), flush=True)
+    elif args.workload == "oscr":
         o = run_oscr(args, rank, world, dev, peaks)
         if rank == 0:
             o.update({"n_gpus": world, "steps": 15, "warmup": 3, "ms_per_step": o["value"], "scaling": "strong", "vs_baseline": None,
@@ -458,7 +529,7 @@ def main():
                     "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                     "config": {"workload": workload_name, "global_batch": cfg["B"] * world, "in_features": cfg["K"],
-                               "classes": cfg["C"], "parallelism": f"batch-sharded x{world}, NCCL all-reduce of fp32 dW" if world > 1 else "single GPU",
+                               "classes": cfg["C"], "parallelism": f"batch-sharded x{world}; {r['allreduce']}" if world > 1 else "single GPU",
                                "l2": "3 rotating 64 MB feature buffers + 64 MB dX + 32 MB dZ per step: working set > 126 MB L2"},
                     "roofline": r["roofline"], "e2e": r["e2e"], "clocks": r["clocks"], "gpu_launches": r["launches"],
                     "loss": r["loss"], "peaks": peaks}

@@ -127,6 +127,27 @@ int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, 
                       void* dx, int64_t lddx, float* dw, float* db,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* ---- multi-GPU: all-reduce of dW over NVLink peer memory, fused with the split-K reduction ----- *
+ * The reference has no collective at all (script/train_all.py:96-118 runs independent jobs); this is what a
+ * batch-sharded head needs instead of `reduce locally, then NCCL`.
+ * osb_head_backward_dw_partials runs only the dW GEMM: `osb_head_dw_splits(B,K,C)` fp32 partial matrices [C,K] are
+ * left at byte offset osb_head_dw_partials_offset() of the workspace, consecutive splits C*K elements apart.
+ * osb_head_dw_allreduce (one launch per rank, every rank must call it with the same epoch): rank r sums slice r of
+ * ALL ranks' partials in a fixed order (bit-identical result on every rank), scales by gscale[0] and stores it
+ * into every rank's dW; `n_extra` floats per rank (db, loss) are summed into extra_out.  The four pointer tables
+ * are HOST arrays of `world` DEVICE pointers to peer-mapped memory (torch.distributed._symmetric_memory):
+ * partial buffers, dW buffers, extra vectors, flag areas of osb_head_dw_allreduce_flag_bytes(world) bytes (zeroed
+ * once).  epoch: non-zero, +1 per call.  A rank that waits ~2 s for a peer gives up and writes the epoch to
+ * flag word [2*world] instead of hanging.  max_ctas bounds the grid (default 32) so the kernel overlaps dX. */
+size_t osb_head_dw_partials_offset(void);
+int osb_head_dw_splits(int64_t B, int K, int C);
+int osb_head_backward_dw_partials(const void* dz, int64_t lddz, const void* x, int64_t ldx, int64_t B, int K, int C,
+                                  void* ws, size_t ws_bytes, void* stream);
+size_t osb_head_dw_allreduce_flag_bytes(int world);
+int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,
+                          void* const* peer_flags, int rank, int world, int splits, int64_t n, int64_t split_stride,
+                          float* extra_out, int n_extra, const float* gscale, uint32_t epoch, int max_ctas, void* stream);
+
 /* ---- confidence (metrics.py:8-42) ---------------------------------------------------------- *
  *   scores [N, ld] float32, y [N] int64.
  *   sums[2]   (double) {sum over known rows of s[i,y_i],

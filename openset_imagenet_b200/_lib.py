@@ -37,6 +37,11 @@ SIGNATURES = {
     "osb_head_forward": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _i64, _p, _i,
                               _p, _p, _p, _p, _p, _p, _p, _i64, _p, _sz, _p]),
     "osb_head_backward": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "osb_head_dw_partials_offset": (_sz, []),
+    "osb_head_dw_splits": (_i, [_i64, _i, _i]),
+    "osb_head_backward_dw_partials": (_i, [_p, _i64, _p, _i64, _i64, _i, _i, _p, _sz, _p]),
+    "osb_head_dw_allreduce_flag_bytes": (_sz, [_i]),
+    "osb_head_dw_allreduce": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _i64, _p, _i, _p, C.c_uint32, _i, _p]),
     "osb_confidence_workspace_bytes": (_sz, [_i64]),
     "osb_confidence": (_i, [_p, _i64, _p, _i64, _i, _f, _i64, _i, _p, _p, _p, _sz, _p]),
     "osb_confidence_from_stats": (_i, [_p, _p, _p, _i64, _i, _f, _i64, _i, _p, _p, _p]),

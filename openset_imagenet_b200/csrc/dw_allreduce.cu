@@ -1,0 +1,186 @@
+// All-reduce of the head's weight gradient over NVLink peer memory, fused with the split-K reduction.
+//
+// The dW GEMM (head_dw_kernel) leaves `splits` fp32 partial matrices in every rank's workspace.  Instead of
+// reducing them locally and handing the result to NCCL, ONE kernel per rank does a two-shot all-reduce straight
+// from the partials: rank r owns the r-th slice of the C*K elements, reads that slice of EVERY rank's partials
+// with peer loads (fixed order: rank 0 split 0, rank 0 split 1, ..., so the sum is deterministic and all ranks end
+// up with bit-identical gradients), scales by g and writes the result into every rank's dW with peer stores.
+// A small `extra` vector per rank (db, loss) is summed by every rank for itself.  Cross-GPU ordering uses
+// epoch-stamped flags in peer memory (st.release.sys / ld.acquire.sys); epochs only grow, nothing is reset.
+//
+// All buffers must be peer-mapped (torch.distributed._symmetric_memory).  The kernel runs on a side stream with a
+// small grid so that it overlaps the dX GEMM.  The reference has no counterpart.
+#include "osb_common.cuh"
+
+namespace osb {
+
+constexpr int kArMaxWorld = 16;
+constexpr int kArThreads = 1024;
+
+struct ArParams {
+    const float* partials[kArMaxWorld];     // [splits][n] per rank
+    float* out[kArMaxWorld];                // [n] per rank (dW)
+    const float* extra_in[kArMaxWorld];     // [n_extra] per rank, nullable
+    unsigned int* flags[kArMaxWorld];       // per rank: [0..W) ready stamps, [W..2W) done stamps, [2W] error word
+    float* extra_out;                       // local [n_extra]
+    const float* gscale;                    // nullable device scalar
+    long long n;                            // elements of dW (multiple of 4)
+    long long split_stride;                 // elements between consecutive splits
+    int n_extra, splits, rank, world;
+    unsigned int epoch;
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
+    float4 r;       // peer memory is not cached in the local L2; keep it out of L1 as well
+    asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+// Wait until flags[i] >= epoch for every i < world (threads 0..world-1 poll one flag each).  Gives up after
+// timeout_cycles and records the failure instead of hanging the GPU.
+__device__ __forceinline__ void wait_stamps(const unsigned int* stamps, unsigned int* err, const ArParams& p) {
+    if (threadIdx.x < p.world) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(stamps + threadIdx.x) - p.epoch) < 0) {
+            if (clock64() - t0 > p.timeout_cycles) { atomicExch(err, p.epoch); break; }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kArThreads)
+dw_allreduce_kernel(const ArParams p) {
+    unsigned int* my_flags = p.flags[p.rank];
+    unsigned int* err = my_flags + 2 * p.world;
+    __shared__ unsigned int s_last;
+    // 1. my partials are complete (stream order: this kernel follows the dW GEMM): tell every rank
+    if (blockIdx.x == 0 && threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch);
+    // 2. wait for every rank's partials
+    wait_stamps(my_flags, err, p);
+    // 3. reduce my slice and publish it everywhere
+    const float gs = p.gscale ? p.gscale[0] : 1.f;
+    const long long n4 = p.n / 4;
+    const long long per = (n4 + p.world - 1) / p.world;
+    const long long lo = per * p.rank, hi = (lo + per < n4) ? lo + per : n4;
+    const long long stride4 = p.split_stride / 4;
+    // All sources (rank 0 split 0, rank 0 split 1, ..., rank 1 split 0, ...) are listed once in shared memory; a thread
+    // takes kElems elements and kBatch sources at a time: 16 independent 16-byte peer loads in flight per thread (a
+    // peer load takes ~2 us), while the sum itself stays in that fixed source order.
+    constexpr int kElems = 2, kBatch = 8;
+    __shared__ const float4* s_src[kArMaxWorld * 16];
+    const int n_src = p.world * p.splits;
+    for (int q = threadIdx.x; q < n_src; q += kArThreads)
+        s_src[q] = reinterpret_cast<const float4*>(p.partials[q / p.splits]) + (long long)(q % p.splits) * stride4;
+    __syncthreads();
+    const long long tstride = (long long)gridDim.x * kArThreads;
+    for (long long i0 = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += tstride * kElems) {
+        float4 acc[kElems];
+#pragma unroll
+        for (int e = 0; e < kElems; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q0 = 0; q0 < n_src; q0 += kBatch) {
+            float4 v[kElems][kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const float4* src = s_src[q0 + j < n_src ? q0 + j : 0];
+#pragma unroll
+                for (int e = 0; e < kElems; ++e) {
+                    const long long i = i0 + e * tstride;
+                    v[e][j] = (i < hi && q0 + j < n_src) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < kElems; ++e) {
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) { acc[e].x += v[e][j].x; acc[e].y += v[e][j].y; acc[e].z += v[e][j].z; acc[e].w += v[e][j].w; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kElems; ++e) {
+            const long long i = i0 + e * tstride;
+            if (i < hi) {
+                acc[e].x *= gs; acc[e].y *= gs; acc[e].z *= gs; acc[e].w *= gs;
+                for (int r = 0; r < p.world; ++r) reinterpret_cast<float4*>(p.out[r])[i] = acc[e];
+            }
+        }
+    }
+    if (blockIdx.x == 0 && p.n_extra > 0) {
+        for (int i = threadIdx.x; i < p.n_extra; i += kArThreads) {
+            float acc = 0.f;
+            for (int r = 0; r < p.world; ++r) {
+                float v;
+                asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(v) : "l"(p.extra_in[r] + i) : "memory");
+                acc += v;
+            }
+            p.extra_out[i] = acc;
+        }
+    }
+    // 4. all my blocks are done: tell every rank (the last block out does it)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int* ticket = my_flags + 2 * p.world + 1;
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.world + p.rank, p.epoch);
+        // 5. my dW is complete once every owner has published its slice; the extras of the other ranks must also
+        //    stay untouched until everybody has read them, which the same stamps guarantee
+        wait_stamps(my_flags + p.world, err, p);
+    }
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+static long long g_ar_timeout = 0;
+// developer hook (not in the public header): shorter give-up time for the tests, 0 = default (~2 s)
+extern "C" void osb_debug_set_allreduce_timeout(long long cycles) { g_ar_timeout = cycles; }
+
+extern "C" size_t osb_head_dw_allreduce_flag_bytes(int world) { return world < 1 ? 0 : sizeof(unsigned int) * (2 * (size_t)world + 8); }
+
+extern "C" int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,
+                                     void* const* peer_flags, int rank, int world, int splits, int64_t n, int64_t split_stride,
+                                     float* extra_out, int n_extra, const float* gscale, uint32_t epoch, int max_ctas, void* stream) {
+    OSB_ENTRY_GUARD();
+    OSB_REQUIRE(peer_partials && peer_dw && peer_flags, OSB_ERR_ARG, "osb_head_dw_allreduce: null pointer table");
+    OSB_REQUIRE(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, OSB_ERR_ARG, "osb_head_dw_allreduce: bad rank %d / world %d", rank, world);
+    OSB_REQUIRE(splits <= 16, OSB_ERR_ARG, "osb_head_dw_allreduce: at most 16 splits (got %d)", splits);
+    OSB_REQUIRE(splits >= 1 && n > 0 && n % 4 == 0 && split_stride >= n && split_stride % 4 == 0, OSB_ERR_ARG,
+                "osb_head_dw_allreduce: bad sizes splits=%d n=%lld stride=%lld", splits, (long long)n, (long long)split_stride);
+    OSB_REQUIRE(n_extra == 0 || (peer_extra && extra_out), OSB_ERR_ARG, "osb_head_dw_allreduce: extras without buffers");
+    OSB_REQUIRE(epoch != 0, OSB_ERR_ARG, "osb_head_dw_allreduce: epoch must be non-zero and grow by one per call");
+    ArParams p = {};
+    for (int r = 0; r < world; ++r) {
+        OSB_REQUIRE(peer_partials[r] && peer_dw[r] && peer_flags[r] && (n_extra == 0 || peer_extra[r]), OSB_ERR_ARG,
+                    "osb_head_dw_allreduce: null peer pointer for rank %d", r);
+        OSB_REQUIRE((uintptr_t)peer_partials[r] % 16 == 0 && (uintptr_t)peer_dw[r] % 16 == 0, OSB_ERR_ARG,
+                    "osb_head_dw_allreduce: peer buffers must be 16-byte aligned");
+        p.partials[r] = reinterpret_cast<const float*>(peer_partials[r]);
+        p.out[r] = reinterpret_cast<float*>(peer_dw[r]);
+        p.extra_in[r] = n_extra ? reinterpret_cast<const float*>(peer_extra[r]) : nullptr;
+        p.flags[r] = reinterpret_cast<unsigned int*>(peer_flags[r]);
+    }
+    p.extra_out = extra_out; p.gscale = gscale; p.n = n; p.split_stride = split_stride;
+    p.n_extra = n_extra; p.splits = splits; p.rank = rank; p.world = world; p.epoch = epoch;
+    p.timeout_cycles = g_ar_timeout > 0 ? g_ar_timeout : 4000000000LL;        // ~2 s at 1.9 GHz
+    int grid = max_ctas > 0 ? max_ctas : 32;
+    const long long work = (n / 4 / world + kArThreads - 1) / kArThreads;
+    if (grid > work) grid = (int)(work < 1 ? 1 : work);
+    dw_allreduce_kernel<<<grid, kArThreads, 0, (cudaStream_t)stream>>>(p);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}

@@ -811,6 +811,7 @@ static int fwd_box_rows(int C) { return C <= 128 ? 128 : 256; }
 using namespace osb;
 using namespace osb::head;
 
+static thread_local bool g_dw_partials_only = false;   // set by osb_head_backward_dw_partials around its call
 static long long* g_trace = nullptr;
 // developer hook (not part of the public header): device buffer of [grid][64] int64 clock stamps, or NULL
 extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<long long*>(p); }
@@ -890,7 +891,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
     OSB_REQUIRE(lddz >= C && lddz % 8 == 0, OSB_ERR_ARG, "osb_head_backward: lddz=%lld must be >= C and a multiple of 8", (long long)lddz);
     OSB_REQUIRE(!dx || (lddx >= K && lddx % 8 == 0), OSB_ERR_ARG, "osb_head_backward: bad lddx=%lld", (long long)lddx);
     OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)dz % 16 == 0) &&
-                ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0), OSB_ERR_ARG,
+                ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0) && ((uintptr_t)ws % 16 == 0), OSB_ERR_ARG,
                 "osb_head_backward: x, w, dz, dx and dw must be 16-byte aligned");
     OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "osb_head_backward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -907,7 +908,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         head_dx_kernel<<<grid, kThreads, kDxSmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
         OSB_LAUNCH_CHECK();
     }
-    if (dw) {
+    if (dw || g_dw_partials_only) {
         CUtensorMap tdz, tx;
         OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 64), "dz (MN-major)");
         OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
@@ -918,17 +919,31 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
         head_dw_kernel<<<units, kThreads, kDwSmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
         OSB_LAUNCH_CHECK();
-        const size_t n4 = (size_t)C * K / 4;
-        int rgrid = (int)((n4 + 255) / 256);
-        const int cap = sm_count() * 8;
-        if (rgrid > cap) rgrid = cap;
-        dw_reduce_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, n4, gscale,
-                                                reinterpret_cast<float4*>(dw));
-        OSB_LAUNCH_CHECK();
+        if (dw) {
+            const size_t n4 = (size_t)C * K / 4;
+            int rgrid = (int)((n4 + 255) / 256);
+            const int cap = sm_count() * 8;
+            if (rgrid > cap) rgrid = cap;
+            dw_reduce_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, n4, gscale,
+                                                    reinterpret_cast<float4*>(dw));
+            OSB_LAUNCH_CHECK();
+        }
     }
     if (db) {
         db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, gscale, db);
         OSB_LAUNCH_CHECK();
     }
     return OSB_OK;
+}
+
+// ---- multi-GPU: the dW GEMM alone (split-K partials stay in the workspace), for the peer-memory all-reduce ----
+extern "C" size_t osb_head_dw_partials_offset(void) { return kWsOffDw; }
+extern "C" int osb_head_dw_splits(int64_t B, int K, int C) { return dw_splits((int)B, K, C); }
+extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, const void* x, int64_t ldx, int64_t B, int K, int C,
+                                             void* ws, size_t ws_bytes, void* stream) {
+    g_dw_partials_only = true;
+    // w is not read by the dW GEMM; x doubles as a valid non-null placeholder for the argument checks
+    const int rc = osb_head_backward(dz, lddz, x, ldx, x, B, K, C, nullptr, nullptr, K, nullptr, nullptr, ws, ws_bytes, stream);
+    g_dw_partials_only = false;
+    return rc;
 }

@@ -94,6 +94,78 @@ class ShardedHead:
         return work, unpack
 
 
+class PeerGradAllReduce:
+    """The head's dW all-reduce over NVLink peer memory, fused with the split-K reduction (``osb_head_dw_allreduce``).
+
+    Every pointer table lists, per rank, the DEVICE address of that rank's buffer as mapped into this process:
+    the head workspace (split-K partials), the packed ``[dW | db | loss]`` buffer, and a small flag area.
+    ``from_symmetric_memory`` builds them with ``torch.distributed._symmetric_memory``; tests on one GPU pass
+    plain pointers.  ``run()`` enqueues ONE kernel on a side stream (after the dW GEMM of the current stream) and
+    returns an event; the result is bit-identical on every rank and deterministic.
+    """
+
+    def __init__(self, plan, ws_ptrs, flat_ptrs, flag_ptrs, rank, world, n_extra, max_ctas=32):
+        from . import _lib as L
+        self._L = L
+        self.plan, self.rank, self.world, self.n_extra, self.max_ctas = plan, int(rank), int(world), int(n_extra), int(max_ctas)
+        off = L.size("osb_head_dw_partials_offset")
+        n = plan.C * plan.K
+        P = L.C.c_void_p * world
+        self._partials = P(*[int(p) + off for p in ws_ptrs])
+        self._dw = P(*[int(p) for p in flat_ptrs])
+        self._extra = P(*[int(p) + 4 * (plan.flat.numel() - n_extra) for p in flat_ptrs])
+        self._flags = P(*[int(p) for p in flag_ptrs])
+        self.splits = L.size("osb_head_dw_splits", plan.B, plan.K, plan.C)
+        self.n = n
+        self.extra_sum = torch.zeros(max(n_extra, 1), dtype=torch.float32, device=plan.dev)
+        self.epoch = 0
+        self.stream = torch.cuda.Stream(device=plan.dev)
+        self._ready = torch.cuda.Event()
+        self._done = torch.cuda.Event()
+        self._keep = None
+
+    @classmethod
+    def from_symmetric_memory(cls, B, K, C, variant, group=None, max_ctas=32, device=None, **plan_kwargs):
+        """Allocates workspace, gradient buffer and flags in symmetric memory, builds the ``HeadPlan`` on them."""
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        from .functional import HeadPlan
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        rank, ws_ = world()
+        grp = group if group is not None else dist.group.WORLD
+        bias = bool(plan_kwargs.get("bias", False))
+        n_flat = C * K + (C if bias else 0) + 1
+        ws_bytes = max(L.size("osb_head_workspace_bytes", B, K, C), L.size("osb_loss_workspace_bytes", B)) + 4096
+        wsb = symm_mem.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        flat = symm_mem.empty(n_flat, dtype=torch.float32, device=dev)
+        flags = symm_mem.empty(L.size("osb_head_dw_allreduce_flag_bytes", ws_) // 4, dtype=torch.int32, device=dev)
+        wsb.zero_(); flat.zero_(); flags.zero_()
+        handles = [symm_mem.rendezvous(t, grp) for t in (wsb, flat, flags)]
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=flat, workspace=wsb, **plan_kwargs)
+        obj = cls(plan, handles[0].buffer_ptrs, handles[1].buffer_ptrs, handles[2].buffer_ptrs, rank, ws_,
+                  n_extra=n_flat - C * K, max_ctas=max_ctas)
+        obj._keep = (wsb, flat, flags, handles)
+        return obj
+
+    def run(self, gscale=None):
+        """dW GEMM partials must already be enqueued on the current stream.  Returns the completion event."""
+        L = self._L
+        cur = torch.cuda.current_stream(self.plan.dev)
+        self._ready.record(cur)
+        self.stream.wait_event(self._ready)
+        self.epoch += 1
+        L.call("osb_head_dw_allreduce", self._partials, self._dw, self._extra if self.n_extra else None, self._flags,
+               self.rank, self.world, self.splits, self.n, self.n, L.ptr(self.extra_sum), self.n_extra, L.ptr(gscale),
+               self.epoch & 0xFFFFFFFF or 1, self.max_ctas, self.stream.cuda_stream)
+        self._done.record(self.stream)
+        return self._done
+
+    def error_word(self, flags_tensor) -> int:
+        return int(flags_tensor[2 * self.world].item())
+
+
 class ShardedHeadPlan:
     """Allocation-free batch-sharded head step (``functional.HeadPlan`` per rank + ONE all-reduce).
 
@@ -105,7 +177,8 @@ class ShardedHeadPlan:
     the forward kernel.
     """
 
-    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=16, device=None, **plan_kwargs):
+    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=32, device=None, peer_allreduce=False,
+                 **plan_kwargs):
         from . import _lib as L
         from .functional import HeadPlan
         self.group = group
@@ -113,8 +186,16 @@ class ShardedHeadPlan:
         self.variant = variant
         bias = bool(plan_kwargs.get("bias", False))
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.flat = torch.zeros(C * K + (C if bias else 0) + 1, dtype=torch.float32, device=dev)
-        self.plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=self.flat, **plan_kwargs)
+        self.peer = None
+        if peer_allreduce and self.world > 1:
+            # dW all-reduce over NVLink peer memory fused with the split-K reduction (no NCCL on the data path)
+            self.peer = PeerGradAllReduce.from_symmetric_memory(B, K, C, variant, group=group, max_ctas=sm_reserve, device=dev,
+                                                                **plan_kwargs)
+            self.plan = self.peer.plan
+            self.flat = self.plan.flat
+        else:
+            self.flat = torch.zeros(C * K + (C if bias else 0) + 1, dtype=torch.float32, device=dev)
+            self.plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=self.flat, **plan_kwargs)
         self._L = L
         self._sms = L.size("osb_sm_count")
         self.sm_reserve = int(sm_reserve) if self.world > 1 else 0
@@ -135,6 +216,15 @@ class ShardedHeadPlan:
         p = self.plan
         p.label_stats(y, self._den_hook)
         p.forward(x, w, y, bias)
+        if self.peer is not None:
+            p.backward_dw_partials(x)
+            done = self.peer.run()
+            self._L.load().osb_set_cta_limit(self._sms - self.sm_reserve)
+            try:
+                p.backward_dx(x, w)
+            finally:
+                self._L.load().osb_set_cta_limit(0)
+            return done
         p.backward_dw(x, w)
         work = None
         if self.world > 1:
@@ -147,10 +237,18 @@ class ShardedHeadPlan:
                 self._L.load().osb_set_cta_limit(0)
         return work
 
-    @staticmethod
-    def finish(work):
-        if work is not None:
+    def finish(self, work):
+        """Make the current stream wait for the gradient all-reduce.  With the peer-memory path the full-batch loss
+        is ``peer.extra_sum[-1]`` (``plan.loss`` keeps this shard's contribution)."""
+        if work is None:
+            return
+        if isinstance(work, torch.cuda.Event):
+            torch.cuda.current_stream(self.plan.dev).wait_event(work)
+        else:
             work.wait()
+
+    def full_loss(self) -> torch.Tensor:
+        return self.peer.extra_sum[self.peer.n_extra - 1] if self.peer is not None else self.plan.loss[0]
 
 
 # ------------------------------------------------------------------------------------------------

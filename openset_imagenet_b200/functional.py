@@ -25,7 +25,8 @@ class HeadPlan:
 
     def __init__(self, B: int, K: int, C: int, variant: str = "entropic", unk_weight: float = 1.0,
                  class_weights: torch.Tensor | None = None, ignore_index: int | None = None,
-                 last_valid_class=None, bias: bool = False, device=None, grad_buffer: torch.Tensor | None = None):
+                 last_valid_class=None, bias: bool = False, device=None, grad_buffer: torch.Tensor | None = None,
+                 workspace: torch.Tensor | None = None):
         if K % 64 != 0:
             raise ValueError("HeadPlan needs in_features % 64 == 0 (FusedOpenSetHead pads other widths)")
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -37,8 +38,13 @@ class HeadPlan:
         self.class_w = None if class_weights is None else class_weights.detach().to(self.dev).float().contiguous()
         d = self.dev
         self.lddz = (C + 7) // 8 * 8
-        self.ws = torch.zeros(max(L.size("osb_head_workspace_bytes", B, K, C), L.size("osb_loss_workspace_bytes", B)) + 4096,
-                              dtype=torch.uint8, device=d)
+        ws_bytes = max(L.size("osb_head_workspace_bytes", B, K, C), L.size("osb_loss_workspace_bytes", B)) + 4096
+        if workspace is None:
+            workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=d)
+        if workspace.dtype != torch.uint8 or workspace.numel() < ws_bytes:
+            raise ValueError(f"workspace must be a zero-filled uint8 tensor of at least {ws_bytes} bytes")
+        self.ws = workspace
+        self.ws_bytes_needed = ws_bytes
         self.den = torch.empty(1, dtype=torch.float64, device=d)
         self.label_counts = torch.empty(4, dtype=torch.int64, device=d)
         # [dW | db | loss] may live in one caller-owned float32 buffer (the packed all-reduce buffer of dist.py), so
@@ -106,6 +112,11 @@ class HeadPlan:
                 self.step(x, w, y, bias, gscale)
         torch.cuda.current_stream(self.dev).wait_stream(side)
         return graph
+
+    def backward_dw_partials(self, x):
+        """Only the dW GEMM: split-K partials stay in the workspace (input of the peer-memory all-reduce)."""
+        L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, self.B, self.K, self.C,
+               L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
     def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False):
         """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches."""

@@ -207,3 +207,89 @@ def test_head_vs_torch_autocast(B, K, C):
     assert e_ours_loss <= max(1e-3, e_ref_loss)
     assert e_ours_dw <= max(1e-3, 1.05 * e_ref_dw)
     assert e_ours_dx <= max(1e-3, 1.05 * e_ref_dx) or e_ours_dx < 4e-3
+
+
+# ---- peer-memory all-reduce of dW (multi-GPU path), exercised on one GPU -----------------------------------------
+def _partials_of(plan):
+    from openset_imagenet_b200 import _lib as L
+    off = L.size("osb_head_dw_partials_offset")
+    splits = L.size("osb_head_dw_splits", plan.B, plan.K, plan.C)
+    n = plan.C * plan.K
+    return plan.ws[off:off + 4 * splits * n].view(torch.float32).view(splits, n).clone()
+
+
+def _run_plan(B, K, C, seed):
+    from openset_imagenet_b200.functional import HeadPlan
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn(B, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(C, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=seed), device=dev)
+    plan = HeadPlan(B, K, C, "entropic", device=dev)
+    plan.label_stats(y)
+    plan.forward(x, w, y)
+    return plan, x, w, y
+
+
+def test_peer_allreduce_world_1_is_the_local_split_k_reduction():
+    from openset_imagenet_b200 import _lib as L
+    from openset_imagenet_b200.dist import PeerGradAllReduce
+    plan, x, w, y = _run_plan(2048, 512, 200, seed=3)
+    plan.backward_dw(x, w)
+    want = plan.dw.clone()
+    loss = plan.loss.clone()
+    plan.dw.zero_()
+    plan.backward_dw_partials(x)
+    flags = torch.zeros(L.size("osb_head_dw_allreduce_flag_bytes", 1) // 4, dtype=torch.int32, device="cuda")
+    ar = PeerGradAllReduce(plan, [plan.ws.data_ptr()], [plan.flat.data_ptr()], [flags.data_ptr()], 0, 1, n_extra=1)
+    for _ in range(3):                                           # epochs 1, 2, 3 on the same flags
+        plan.dw.zero_()
+        torch.cuda.current_stream().wait_event(ar.run())
+        torch.cuda.synchronize()
+        assert torch.equal(plan.dw, want)
+        assert torch.equal(ar.extra_sum[:1], loss)
+    assert ar.error_word(flags) == 0
+
+
+def test_peer_allreduce_two_emulated_ranks_sum_in_fixed_order():
+    """Ranks run one after the other on ONE GPU with the peer's stamps pre-set (kernels that wait on each other
+    must not share a GPU): every rank reduces its slice of both ranks' partials and writes it to both gradients."""
+    from openset_imagenet_b200 import _lib as L
+    from openset_imagenet_b200.dist import PeerGradAllReduce
+    B, K, C = 1024, 256, 136
+    plans = []
+    for r in range(2):
+        plan, x, w, y = _run_plan(B, K, C, seed=10 + r)
+        plan.backward_dw_partials(x)
+        plans.append(plan)
+    torch.cuda.synchronize()
+    parts = [_partials_of(p) for p in plans]
+    acc = torch.zeros(C * K, device="cuda")
+    for r in range(2):
+        for s in range(parts[r].shape[0]):
+            acc = acc + parts[r][s]                              # the kernel's order: rank 0 split 0, split 1, ..., rank 1 ...
+    losses = [p.loss.clone() for p in plans]
+    nfl = L.size("osb_head_dw_allreduce_flag_bytes", 2) // 4
+    flags = [torch.zeros(nfl, dtype=torch.int32, device="cuda") for _ in range(2)]
+    ws_ptrs = [p.ws.data_ptr() for p in plans]
+    flat_ptrs = [p.flat.data_ptr() for p in plans]
+    flag_ptrs = [f.data_ptr() for f in flags]
+    for r in range(2):
+        peer = 1 - r
+        flags[r][peer] = 1                                       # "peer's partials are ready"
+        flags[r][2 + peer] = 1                                   # "peer has published its slice"
+        ar = PeerGradAllReduce(plans[r], ws_ptrs, flat_ptrs, flag_ptrs, r, 2, n_extra=1)
+        torch.cuda.current_stream().wait_event(ar.run())
+        torch.cuda.synchronize()
+        assert ar.error_word(flags[r]) == 0
+        assert torch.equal(ar.extra_sum[:1], losses[0] + losses[1])
+    for p in plans:                                              # both gradients complete and bit-identical
+        assert torch.equal(p.dw.reshape(-1), acc)
+    # a rank whose peer never shows up gives up instead of hanging (stamps of epoch 2 are missing)
+    ar = PeerGradAllReduce(plans[0], ws_ptrs, flat_ptrs, flag_ptrs, 0, 2, n_extra=1)
+    ar.epoch = 1
+    L.load().osb_debug_set_allreduce_timeout(20_000_000)         # ~10 ms
+    torch.cuda.current_stream().wait_event(ar.run())
+    torch.cuda.synchronize()
+    L.load().osb_debug_set_allreduce_timeout(0)
+    assert ar.error_word(flags[0]) == 2
