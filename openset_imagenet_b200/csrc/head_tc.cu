@@ -179,7 +179,9 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+    // CL consecutive CTAs form a group that shares the rows and splits the classes.  Not a hardware cluster: clusters of
+    // 4 strand ~16 of the 148 SMs (GPC packing); the group only needs co-residency, which the cooperative launch gives.
+    const uint32_t rank = (CL > 1) ? (blockIdx.x % CL) : 0u;
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int n_tiles = (a.B + BM - 1) / BM;
     const int n_kb = (a.K + BK - 1) / BK;
@@ -199,7 +201,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before_sync();
-    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_slot;
 
@@ -473,7 +475,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
     }
     tc_fence_before_sync();
-    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     if (CL > 1 && threadIdx.x < 8) a.xch_flags[((size_t)(cluster_id * 2 + (threadIdx.x >> 2)) * CL + rank) * 4 + (threadIdx.x & 3)] = 0u;
     if (warp == 1) tmem_dealloc(tbase, Cfg::kTmemCols);
 }
@@ -773,22 +775,16 @@ static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, __nv_bfloa
     cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
+    // persistent kernel, one CTA per SM, launched cooperatively when CTAs wait on each other (CL > 1): every CTA of a
+    // group must be resident while its peers spin on its statistics flags
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = CL > 1 ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    // persistent kernel: one wave of clusters.  Clusters must sit inside one GPC, so fewer than SMs/CL may be
-    // co-resident (a 4-CTA cluster strands ~16 of the 148 SMs); ask the runtime once per configuration.
-    static int resident = 0;
-    if (resident == 0) {
-        int n = 0;
-        if (CL > 1 && cudaOccupancyMaxActiveClusters(&n, k, &cfg) == cudaSuccess && n > 0) resident = n;
-        else { cudaGetLastError(); resident = sm_count() / CL; }
-    }
-    int clusters = resident;
-    if (clusters > n_tiles) clusters = n_tiles;
-    if (clusters < 1) clusters = 1;
-    cfg.gridDim = dim3(clusters * CL);
+    int groups = cta_limit() / CL;
+    if (groups > n_tiles) groups = n_tiles;
+    if (groups < 1) groups = 1;
+    cfg.gridDim = dim3(groups * CL);
     OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, dz, lddz, a));
     return OSB_OK;
 }

@@ -661,8 +661,8 @@ oscr_curve_kernel(const CurveParams p) {
     }
     __syncthreads();
     if (sh.tile_tot[0]) {
-        for (int i = tid; i < 4 * kRadix * kMaxGroups; i += kCvThreads)
-            if (((i / kRadix) % kMaxGroups) < (int)NG) p.gsum[i] = 0u;
+        const int used = (int)NG * kRadix;                       // entries touched per pass: groups [0, NG) x 256 digits
+        for (int i = tid; i < 4 * used; i += kCvThreads) p.gsum[(size_t)(i / used) * kMaxGroups * kRadix + (i % used)] = 0u;
         if (p.totals_in && tid < 4) p.totals_in[tid] = 0ull;
         if (tid == 0) { p.sync[0] = 0u; p.sync[1] = 0u; }
     }
