@@ -325,7 +325,7 @@ def run_oscr(args, rank, world, dev, peaks):
         def run(i):
             return calculate_oscr_sharded(gt, bufs[i % len(bufs)], -1)
     else:
-        plan = OscrPlan(N, C, -1, device=dev)
+        plan = OscrPlan(N, C, -1, device=dev, counts=False)      # the reference's outputs: ccr, fpr (float64)
         # the two launches of one evaluation replayed from a CUDA graph (one graph per input buffer): no per-call
         # host work between the row reduce and the cooperative sort + scan kernel
         graphs = []
@@ -371,6 +371,8 @@ def run_oscr(args, rank, world, dev, peaks):
     out = {"metric": "OSCR ms @1M scores", "value": ms, "unit": "ms", "higher_is_better": False, "iters": iters,
            "config": {"workload": f"OSCR CCR/FPR over N={N} x C={C} float32 scores, 50% known / 25% -1 / 25% -2, unk_label=-1",
                       "rows_per_gpu": n_loc, "n_thresholds": n_thr,
+                      "outputs": "ccr, fpr float64 [n_thresholds] as util.calculate_oscr returns them" if world == 1 else
+                                 "ccr, fpr float64 plus thresholds and int64 counts",
                       "l2": "two alternating score buffers, each larger than L2; no flush writes",
                       "launch": "CUDA-graph replay of the two kernels" if world == 1 else "eager (torch.distributed collectives between the stages)"},
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",

@@ -191,8 +191,8 @@ int osb_confidence_from_stats(const float* p_target, const float* p_max, const i
  *   Counts at a fixed threshold are additive across row shards: a shard passes its own unk records plus
  *   ALL shards' known records (remote ones demoted to type 0), then sums ccr_cnt / fpr_cnt over shards.
  *   ONE cooperative launch (all CTAs co-resident; grid barriers through L2).
- * osb_oscr = A + B on one GPU (two launches); meta[4] = n_bad.  osb_oscr_ratios: counts -> float64 ratios
- *   after a cross-shard sum.
+ * osb_oscr = A + B on one GPU (two launches); meta[4] = n_bad.  taus / ccr_cnt / fpr_cnt may be NULL when only the
+ *   reference's own outputs (ccr, fpr) are wanted.  osb_oscr_ratios: counts -> float64 ratios after a cross-shard sum.
  */
 size_t osb_oscr_workspace_bytes(int64_t N);
 size_t osb_oscr_curve_workspace_bytes(int64_t cap);

@@ -266,6 +266,7 @@ constexpr int kMaxGroups = 64;                   // fixed-size group-sum table: 
 constexpr int kTraceSlots = 32;
 constexpr int kQuarters = kCvThreads / kRadix;   // 4
 constexpr int kWarpsPerQuarter = kCvWarps / kQuarters;
+static_assert(kCvWarps == 32, "the second-level scans take one lane per warp");
 static_assert(kCvThreads % kRadix == 0 && kCvWarps % kQuarters == 0, "block shape");
 
 struct CurveParams {
@@ -562,13 +563,17 @@ oscr_curve_kernel(const CurveParams p) {
         if (lane == 31) { sh.wscan[0][warp] = iE; sh.wscan[1][warp] = iC; sh.wscan[2][warp] = iU; }
         if (lane == 0) sh.wsum_l[warp] = sK;
         __syncthreads();
-        uint32_t oE = 0, oC = 0, oU = 0;
+        // second level: warps 0..3 scan the per-warp totals of one quantity each with shuffles (kCvWarps == 32 lanes)
+        if (warp < 4) {
+            const uint32_t v = warp < 3 ? sh.wscan[warp][lane] : sh.wsum_l[lane];
+            uint32_t inc = v;
 #pragma unroll
-        for (int w = 0; w < kCvWarps; ++w) if (w < warp) { oE += sh.wscan[0][w]; oC += sh.wscan[1][w]; oU += sh.wscan[2][w]; }
-        eE = oE + iE - cE; eC = oC + iC - cC; eU = oU + iU - cU;
-        if (tid == kCvThreads - 1) { sh.tile_tot[0] = eE + cE; sh.tile_tot[1] = eC + cC; sh.tile_tot[2] = eU + cU; }
-        if (tid == 0) { uint32_t k = 0; for (int w = 0; w < kCvWarps; ++w) k += sh.wsum_l[w]; sh.tile_tot[3] = k; }
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += a; }
+            if (warp < 3) sh.wscan[warp][lane] = inc - v;          // exclusive prefix of the warp totals
+            if (lane == 31) sh.tile_tot[warp] = inc;               // tile totals: thresholds, correct, unk, known
+        }
         __syncthreads();
+        eE = sh.wscan[0][warp] + iE - cE; eC = sh.wscan[1][warp] + iC - cC; eU = sh.wscan[2][warp] + iU - cU;
     };
     stamp(24);
     for (int64_t t = g; t < T; t += G) {
@@ -640,8 +645,8 @@ oscr_curve_kernel(const CurveParams p) {
             const int64_t j = j0 + i;
             const int64_t c_gt = s_cc[i], u_gt = sh.stage_u[i];
             if (p.taus) p.taus[j] = key_to_float(s_key[i]);
-            p.ccr_cnt[j] = c_gt;
-            p.fpr_cnt[j] = u_gt;
+            if (p.ccr_cnt) p.ccr_cnt[j] = c_gt;
+            if (p.fpr_cnt) p.fpr_cnt[j] = u_gt;
             if (p.ccr) p.ccr[j] = exact_div((double)c_gt, d_known, r_known);   // util.py:114
             if (p.fpr) p.fpr[j] = exact_div((double)u_gt, d_unk, r_unk);       // util.py:117 (0/0 -> NaN like numpy)
         }
@@ -949,7 +954,7 @@ extern "C" int osb_oscr_curve(const uint64_t* rec_a, const int64_t* n_a, const u
     OSB_REQUIRE(meta && ws, OSB_ERR_ARG, "osb_oscr_curve: null pointer");
     OSB_REQUIRE(cap >= 0 && cap < (1LL << 30), OSB_ERR_ARG, "osb_oscr_curve: bad cap=%lld", (long long)cap);
     OSB_REQUIRE((!rec_a || n_a) && (!rec_b || n_b), OSB_ERR_ARG, "osb_oscr_curve: record array without its count");
-    OSB_REQUIRE(cap == 0 || (ccr_cnt && fpr_cnt), OSB_ERR_ARG, "osb_oscr_curve: null count outputs");
+    OSB_REQUIRE(cap == 0 || (ccr_cnt && fpr_cnt) || (ccr && fpr), OSB_ERR_ARG, "osb_oscr_curve: needs the count outputs or the ratio outputs");
     OSB_REQUIRE(ws_bytes >= curve_ws_bytes(cap), OSB_ERR_WORKSPACE, "osb_oscr_curve: workspace too small (%zu < %zu)", ws_bytes, curve_ws_bytes(cap));
     return run_curve(rec_a, rec_a ? n_a : nullptr, rec_b, rec_b ? n_b : nullptr, cap, taus, ccr_cnt, fpr_cnt, ccr, fpr, meta, nullptr,
                      ws, (cudaStream_t)stream);
@@ -977,7 +982,7 @@ extern "C" int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_
     OSB_REQUIRE(meta && ws, OSB_ERR_ARG, "osb_oscr: null pointer");
     int rc = check_oscr_sizes("osb_oscr", N, C, ld);
     if (rc) return rc;
-    OSB_REQUIRE(N == 0 || (scores && gt && taus && ccr_cnt && fpr_cnt && ccr && fpr), OSB_ERR_ARG, "osb_oscr: null pointer");
+    OSB_REQUIRE(N == 0 || (scores && gt && ccr && fpr), OSB_ERR_ARG, "osb_oscr: null pointer");
     OSB_REQUIRE(ws_bytes >= osb_oscr_workspace_bytes(N), OSB_ERR_WORKSPACE, "osb_oscr: workspace too small (%zu < %zu)",
                 ws_bytes, osb_oscr_workspace_bytes(N));
     cudaStream_t st = (cudaStream_t)stream;

@@ -138,13 +138,15 @@ class OscrPlan:
 
     _LABELS = {torch.int64: L.LABEL_I64, torch.float32: L.LABEL_F32, torch.int32: L.LABEL_I32}
 
-    def __init__(self, N: int, C: int, unk_label: int = -1, device=None):
+    def __init__(self, N: int, C: int, unk_label: int = -1, device=None, counts: bool = True):
+        """``counts=False`` computes only what ``util.calculate_oscr`` of the reference returns (ccr, fpr); the
+        thresholds and the integer counts behind them (``taus``, ``ccr_cnt``, ``fpr_cnt``) are then ``None``."""
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.N, self.C, self.unk_label = int(N), int(C), int(unk_label)
         d, cap = self.dev, max(int(N), 1)
-        self.taus = torch.empty(cap, dtype=torch.float32, device=d)
-        self.ccr_cnt = torch.empty(cap, dtype=torch.int64, device=d)
-        self.fpr_cnt = torch.empty(cap, dtype=torch.int64, device=d)
+        self.taus = torch.empty(cap, dtype=torch.float32, device=d) if counts else None
+        self.ccr_cnt = torch.empty(cap, dtype=torch.int64, device=d) if counts else None
+        self.fpr_cnt = torch.empty(cap, dtype=torch.int64, device=d) if counts else None
         self.ccr = torch.empty(cap, dtype=torch.float64, device=d)
         self.fpr = torch.empty(cap, dtype=torch.float64, device=d)
         self.meta = torch.zeros(5, dtype=torch.int64, device=d)

@@ -261,3 +261,19 @@ def test_ccr_at_fpr_ties_nan_and_empty():
     assert osb.ccr_at_fpr(np.array([0.1, 0.2]), nan_fpr, [0.1])[0][0] == 0
     with pytest.raises(ValueError):
         osb.ccr_at_fpr(np.array([]), np.array([]), [0.1])
+
+
+def test_oscr_plan_with_and_without_count_outputs():
+    """OscrPlan(counts=False) writes only the reference's outputs (ccr, fpr); both modes agree bit for bit."""
+    from openset_imagenet_b200.functional import OscrPlan
+    gt, s = O.make_oscr_case(60_000, 116, seed=14)
+    o_ccr, o_fpr = O.calculate_oscr(gt, s, -1)
+    st, gtt = torch.tensor(s, device="cuda"), torch.tensor(gt, device="cuda")
+    full = OscrPlan(60_000, 116, -1).run(st, gtt)
+    lean = OscrPlan(60_000, 116, -1, counts=False).run(st, gtt)
+    assert lean.taus is None and lean.ccr_cnt is None and lean.fpr_cnt is None
+    assert lean.meta.tolist() == full.meta.tolist()
+    n = int(lean.meta[0]) - 1
+    for r in (full, lean):
+        np.testing.assert_array_equal(r.ccr[:n].cpu().numpy(), o_ccr)
+        np.testing.assert_array_equal(r.fpr[:n].cpu().numpy(), o_fpr)
