@@ -607,6 +607,135 @@ head_dx_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
 }
 
 // =================================================================================================
+// dX with CTA pairs (cta_group::2): one cluster of 2 CTAs per 256 rows x 256 features, M = 256 MMAs.
+// CTA r of the pair loads rows [128 r, +128) of the dZ tile and features [128 r, +128) of the W tile (32 KB per stage
+// instead of 48 KB), the leader issues the MMAs, each CTA drains its own 128 x 256 accumulator from its TMEM.
+// =================================================================================================
+constexpr int kDx2Stages = 6;
+constexpr int kDx2StageBytes = kABytes + 2 * kBoxBytes;         // 32 KB per CTA
+constexpr int kDx2OffStage = kDx2Stages * kDx2StageBytes;
+constexpr int kDx2OffBars = kDx2OffStage + 4 * 2 * kStageWarpBytes;
+constexpr int kDx2SmemBytes = kDx2OffBars + (2 * kDx2Stages + 4) * 8 + 16 + 1024;
+static_assert(kDx2SmemBytes <= 232448, "dx2 kernel shared memory");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_w,
+                const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, const float* __restrict__ gscale) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* sStage = smem + kDx2OffStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDx2OffBars);
+    uint64_t* full = bars; uint64_t* empty = full + kDx2Stages;
+    uint64_t* t_full = empty + kDx2Stages; uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank_();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDx2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }     // 4 epilogue warps x 2 CTAs
+        fence_barrier_init();
+        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dx);
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 512);
+    tc_fence_before_sync();
+    cluster_sync_();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const int m_tiles = (B + 255) / 256, n_tiles = (K + kDxBN - 1) / kDxBN;
+    const int total = m_tiles * n_tiles;
+    const int n_kb = (C + BK - 1) / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = pair; tile < total; tile += n_pairs) {
+                const int mt = tile / n_tiles, nt = tile % n_tiles;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDx2StageBytes);     // both CTAs' bytes land on the leader's barrier
+                    uint8_t* st = smem + s * kDx2StageBytes;
+                    tma_load_2d_2sm(st, &tm_dz, &full[s], kb * BK, mt * 256 + rank * 128);               // 64 classes x 128 rows
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)                                                         // 64 features x 64 classes
+                        tma_load_2d_2sm(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kb * BK);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(256, kDxBN, false, true);
+            uint32_t it = 0, tc = 0;
+            for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
+                const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+                mbar_wait(&t_empty[buf], tph ^ 1);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + s * kDx2StageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+                    const int rem = C - kb * BK;
+                    const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+                    for (int k = 0; k < ksteps; ++k)
+                        umma2_bf16(tbase + buf * kDxBN, make_desc_kmajor(a_addr + k * 32),
+                                   make_desc_mnmajor(b_addr + k * 2048, kBoxBytes), idesc, (kb | k) != 0);
+                    umma2_commit_mc(&empty[s]);
+                }
+                umma2_commit_mc(&t_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
+        const float gs = gscale ? gscale[0] : 1.f;
+        uint32_t tc = 0, n_stores = 0;
+        for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
+            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+            mbar_wait(&t_full[buf], tph);
+            tc_fence_after_sync();
+            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kDxBN; c0 += 64) {
+                uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0 + h * 32, v);
+                    tmem_ld_wait();
+                    float g[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[i]);
+#pragma unroll
+                    for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_dx, sbuf, nt * kDxBN + c0, mt * 256 + rank * 128 + q * 32);
+                    tma_store_commit();
+                }
+                ++n_stores;
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&t_empty[buf]);
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+    tc_fence_before_sync();
+    cluster_sync_();
+    if (warp == 1) tmem_dealloc2(tbase, 512);
+}
+
+// =================================================================================================
 // dW partials = dZ^T X over a slice of the batch: both operands MN-major views of row-major tiles
 // =================================================================================================
 constexpr int kDwBN = 256;
@@ -807,6 +936,9 @@ static int fwd_box_rows(int C) { return C <= 128 ? 128 : 256; }
 using namespace osb;
 using namespace osb::head;
 
+static int g_head_pairs = 1;          // 1: GEMMs run on CTA pairs (cta_group::2) where a pair kernel exists; 0: single-CTA kernels
+// developer hook (not part of the public header): A/B switch between the single-CTA and the CTA-pair kernels
+extern "C" void osb_debug_set_head_pairs(int on) { g_head_pairs = on; }
 static thread_local bool g_dw_partials_only = false;   // set by osb_head_backward_dw_partials around its call
 static long long* g_trace = nullptr;
 // developer hook (not part of the public header): device buffer of [grid][64] int64 clock stamps, or NULL
@@ -896,13 +1028,23 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, BM), "dz (K-major)");
         OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, 64), "w (MN-major)");
         OSB_TMAP(make_tmap_bf16(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx");
-        rc = set_smem(head_dx_kernel, kDxSmemBytes);
-        if (rc) return rc;
-        const int total = (int)((B + BM - 1) / BM) * ((K + kDxBN - 1) / kDxBN);
-        int grid = cta_limit();
-        if (grid > total) grid = total;
-        head_dx_kernel<<<grid, kThreads, kDxSmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
-        OSB_LAUNCH_CHECK();
+        if (g_head_pairs) {
+            rc = set_smem(head_dx2_kernel, kDx2SmemBytes);
+            if (rc) return rc;
+            const int total2 = (int)((B + 255) / 256) * ((K + kDxBN - 1) / kDxBN);
+            int pairs = cta_limit() / 2;
+            if (pairs > total2) pairs = total2;
+            head_dx2_kernel<<<pairs * 2, kThreads, kDx2SmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
+            OSB_LAUNCH_CHECK();
+        } else {
+            rc = set_smem(head_dx_kernel, kDxSmemBytes);
+            if (rc) return rc;
+            const int total = (int)((B + BM - 1) / BM) * ((K + kDxBN - 1) / kDxBN);
+            int grid = cta_limit();
+            if (grid > total) grid = total;
+            head_dx_kernel<<<grid, kThreads, kDxSmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
+            OSB_LAUNCH_CHECK();
+        }
     }
     if (dw || g_dw_partials_only) {
         CUtensorMap tdz, tx;

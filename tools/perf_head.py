@@ -47,7 +47,15 @@ def head_case(B, K, C, variant="entropic"):
     def step(): lab(); fwd(); bdx(); bdw()
     fl = 2.0 * B * K * C
     print(f"--- head B={B} K={K} C={C} {variant}: GEMM flops each {fl/1e9:.2f} GF")
-    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dw(K3+reduce)", bdw, fl), ("step", step, 3 * fl)]:
+    lib = L.load()
+    def bdx1():
+        lib.osb_debug_set_head_pairs(0); bdx(); lib.osb_debug_set_head_pairs(1)
+    def bdw1():
+        lib.osb_debug_set_head_pairs(0); bdw(); lib.osb_debug_set_head_pairs(1)
+    def fwd1():
+        lib.osb_debug_set_head_pairs(0); fwd(); lib.osb_debug_set_head_pairs(1)
+    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd 1-CTA", fwd1, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dx 1-CTA", bdx1, fl),
+                        ("dw(K3+reduce)", bdw, fl), ("dw 1-CTA", bdw1, fl), ("step", step, 3 * fl)]:
         med, mn = timeit(fn)
         med2, mn2 = timeit(fn, flush_l2=False)
         print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | warm med {med2:9.1f} us" + (f" | {f/med/1e6:8.1f} TF/s cold, {f/med2/1e6:8.1f} warm" if f else ""))
