@@ -32,13 +32,12 @@ constexpr int kBoxBytes = 64 * BK * 2;  // 8 KB: 64 rows x 128 B
 constexpr int kStageWarpBytes = 32 * 128;   // epilogue staging: 32 rows x 128 B per warp
 constexpr int kMaxPartials = 2048;
 constexpr size_t kHeadTicketBytes = 128;
-constexpr int kMaxClusters = 148;
-constexpr size_t kXchFlagBytes = (size_t)kMaxClusters * 2 * 4 * 4 * sizeof(unsigned int);
-constexpr size_t kXchStatBytes = (size_t)kMaxClusters * 2 * 4 * 128 * 6 * sizeof(float);
-// workspace: [ticket][loss partials][exchange flags][exchange statistics][dW partials]
+constexpr int kMaxXid = 80;             // row blocks that exchange statistics at the same time: <= 148 / 2 CTAs
+constexpr size_t kXchStatBytes = (size_t)kMaxXid * 2 * 4 * 128 * 6 * sizeof(uint2);
+// workspace (zeroed once by the caller): [ticket, exchange epoch][loss partials][exchange statistics][dW partials]
+constexpr size_t kWsOffEpoch = 64;
 constexpr size_t kWsOffPartials = kHeadTicketBytes;
-constexpr size_t kWsOffFlags = kWsOffPartials + sizeof(double) * kMaxPartials;
-constexpr size_t kWsOffStats = kWsOffFlags + kXchFlagBytes;
+constexpr size_t kWsOffStats = kWsOffPartials + sizeof(double) * kMaxPartials;
 constexpr size_t kWsOffDw = (kWsOffStats + kXchStatBytes + 255) / 256 * 256;
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -71,12 +70,14 @@ __device__ __forceinline__ void st_peer_v2(uint32_t raddr, float a, float b) {
 __device__ __forceinline__ void mbar_arrive_peer(uint32_t raddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(raddr) : "memory");
 }
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+// 8-byte (value, epoch) words: a reader that sees the epoch it waits for has the value that was stored with it
+// (aligned 8-byte accesses are single-copy atomic), so data and flag travel in ONE L2 round trip and need no fence.
+__device__ __forceinline__ void st_ll(uint2* p, float v, uint32_t epoch) {
+    asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -112,42 +113,66 @@ struct FwdArgs {
     float* row_ptgt; float* row_pmax; float* row_pmax_all; int32_t* row_pred;
     int write_dz;
     double* partials; unsigned int* ticket;
-    float* xch_stats;          // [clusters][2][CL][128][6]  per-row statistics exchanged between the CTAs of a cluster
-    unsigned int* xch_flags;   // [clusters][2][CL][4]       release/acquire flags (tile counter), zero between launches
+    uint2* xch_stats;          // [row block][2][CL][128][6] (value, epoch) words: per-row statistics exchanged between the units of a group
+    unsigned int* xch_epoch;   // epochs used so far on this workspace; only grows, so stale words never match
     long long* trace;      // optional [gridDim.x][64] clock stamps (developer tool, NULL in production)
 };
 
 constexpr int kStatFloats = 6;          // m, s, zy, sumz, mv, argmax  (per row, per column slice)
 
 // One CTA owns 128 rows x BN classes of the logits (BN = 128 or 256 TMEM columns, double-buffered so the
-// epilogue of tile t overlaps the MMAs of tile t+1).  Heads wider than BN run as a cluster of CL = ceil(C/BN)
-// CTAs (CL <= 4) that share the rows, split the classes and exchange per-row softmax statistics through DSMEM.
+// epilogue of tile t overlaps the MMAs of tile t+1).  Heads wider than BN run as a group of CL = ceil(C/BN)
+// units (CL <= 4) that share the rows, split the classes and exchange per-row softmax statistics through L2.
 // EW epilogue warps per TMEM lane quadrant each own a slice of the CTA's columns.
-template <int BN, int CL, int STAGES, int EW>
+// PAIR: a unit is a 2-CTA cluster issuing M = 256 MMAs (cta_group::2): CTA r of the pair stages rows [128 r, +128)
+// of a 256-row X tile and half of the unit's W rows, i.e. 32 KB instead of 48 KB per k-block and CTA for the same
+// flops — the single-CTA kernel is bound by L2 -> SM operand traffic (~11.5 TB/s), not by the tensor pipe.
+// Each CTA still drains its own 128 x BN accumulator, so the epilogue is the same code in both modes.
+template <int BN, int CL, int STAGES, int EW, bool PAIR>
 struct FwdCfg {
     static constexpr int kThreads = (2 + 4 * EW) * 32;
     static constexpr int kEpiThreads = 4 * EW * 32;
-    static constexpr int kStageBytes = kABytes + BN * BK * 2;
+    static constexpr int kWRows = PAIR ? BN / 2 : BN;                              // W rows this CTA stages per k-block
+    static constexpr int kStageBytes = kABytes + kWRows * BK * 2;
     static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kTileRows = PAIR ? 2 * BM : BM;                           // rows per tile of a CTA pair / a CTA
     static constexpr int kPeers = CL > 1 ? CL - 1 : 1;
-    static constexpr int kOffLx = STAGES * kStageBytes;                            // [2][EW][128][6] floats
-    static constexpr int kOffPx = kOffLx + 2 * EW * BM * kStatFloats * 4;          // [2][CL-1][128][6] floats
-    static constexpr int kOffBias = kOffPx + 2 * kPeers * BM * kStatFloats * 4;    // [BN] floats
+    static constexpr int kOffDz = STAGES * kStageBytes;                            // [4 EW warps][2] boxes of 32 rows x 128 B (grad-logits staging)
+    static constexpr int kOffLx = kOffDz + 4 * EW * 2 * kStageWarpBytes;           // [2][EW][128][6] floats
+    static constexpr int kOffG = kOffLx + 2 * EW * BM * kStatFloats * 4;           // [2][128][2] floats: row max / sum of the whole head
+    static constexpr int kOffBias = kOffG + 2 * BM * 2 * 4;                        // [BN] floats
+    static constexpr int kGroups = BN / 32 / EW;                                   // 32-column groups per epilogue thread
     static constexpr int kOffBars = kOffBias + BN * 4;
-    static constexpr int kNumBars = 2 * STAGES + 4 + 2;
+    static constexpr int kNumBars = 2 * STAGES + 4;
     static constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;  // + tmem slot + alignment slack
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
-__device__ __forceinline__ float max32(const float (&z)[32]) {
+__device__ __forceinline__ float max32(const uint32_t (&z)[32]) {
     float t[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = fmaxf(z[i], z[i + 16]);
+    for (int i = 0; i < 16; ++i) t[i] = fmaxf(__uint_as_float(z[i]), __uint_as_float(z[i + 16]));
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = fmaxf(t[i], t[i + 8]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) t[i] = fmaxf(t[i], t[i + 4]);
     return fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+}
+
+// v[idx] for a per-thread idx in [0, 32): registers cannot be indexed dynamically, so a 5-level select tree on the bits of
+// idx (31 selects) replaces 32 compare + select pairs.
+__device__ __forceinline__ float select32(const uint32_t (&v)[32], int idx) {
+    uint32_t t[16];
+    const bool b0 = idx & 1, b1 = idx & 2, b2 = idx & 4, b3 = idx & 8, b4 = idx & 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = b0 ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = b1 ? t[2 * j + 1] : t[2 * j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = b2 ? t[2 * j + 1] : t[2 * j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) t[j] = b3 ? t[2 * j + 1] : t[2 * j];
+    return __uint_as_float(b4 ? t[1] : t[0]);
 }
 
 // 8 fp32 -> 8 bf16 -> one 16-byte global store
@@ -162,186 +187,232 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float* f) 
     *reinterpret_cast<uint4*>(dst) = u;
 }
 
-template <int BN, int CL, int STAGES, int EW, bool HAS_BIAS, bool WANT_PRED>
+// 10 warps get 168 registers each: the register file is handed out in 4-warp granules, so 320 threads are budgeted as 384
+// (a 200-register build fails to launch).
+template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED>
 __global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                __nv_bfloat16* __restrict__ dz, int64_t lddz, const FwdArgs a) {
-    using Cfg = FwdCfg<BN, CL, STAGES, EW>;
+                const __grid_constant__ CUtensorMap tm_dz, const FwdArgs a) {
+    using Cfg = FwdCfg<BN, CL, STAGES, EW, PAIR>;
+    constexpr int TM = Cfg::kTileRows;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
+    uint8_t* sDz = smem + Cfg::kOffDz;
     float* sLx = reinterpret_cast<float*>(smem + Cfg::kOffLx);
-    float* sPx = reinterpret_cast<float*>(smem + Cfg::kOffPx);
+    float* sG = reinterpret_cast<float*>(smem + Cfg::kOffG);
     float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
     uint64_t* full = bars;                uint64_t* empty = full + STAGES;
     uint64_t* t_full = empty + STAGES;    uint64_t* t_empty = t_full + 2;
-    uint64_t* x_bar = t_empty + 2;        // [2] statistics exchange with the peer CTAs (cluster only)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // CL consecutive CTAs form a group that shares the rows and splits the classes.  Not a hardware cluster: clusters of
-    // 4 strand ~16 of the 148 SMs (GPC packing); the group only needs co-residency, which the cooperative launch gives.
-    const uint32_t rank = (CL > 1) ? (blockIdx.x % CL) : 0u;
-    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-    const int n_tiles = (a.B + BM - 1) / BM;
+    // A unit is one CTA, or one 2-CTA cluster (PAIR; cr = this CTA's half of the unit's rows).  CL consecutive units
+    // form a group that shares the rows and splits the classes.  The group is not a hardware cluster: clusters of 4
+    // strand ~16 of the 148 SMs (GPC packing); it only needs co-residency, which the cooperative launch gives.
+    const int cr = PAIR ? (int)cluster_ctarank_() : 0;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t rank = (CL > 1) ? (uint32_t)(unit % CL) : 0u;
+    const int cluster_id = unit / CL, n_clusters = n_units / CL;
+    const int xid = PAIR ? cluster_id * 2 + cr : cluster_id;      // slot of this CTA's rows in the exchange buffers
+    const int n_tiles = (a.B + TM - 1) / TM;
     const int n_kb = (a.K + BK - 1) / BK;
-    const int n0 = (int)rank * BN;                        // class range of this CTA
+    const int n0 = (int)rank * BN;                        // class range of this unit
     int ncols = a.C - n0;
     ncols = ncols < 0 ? 0 : (ncols > BN ? BN : ncols);
-    const int ncols16 = (ncols + 15) & ~15;               // UMMA N granularity
+    // UMMA N: multiple of 16 (of 32 for a pair, whose CTAs each stage N / 2 rows of W)
+    const int ncolsN = PAIR ? ((ncols + 31) & ~31) : ((ncols + 15) & ~15);
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * EW); }
-        mbar_init(&x_bar[0], 4 * Cfg::kPeers); mbar_init(&x_bar[1], 4 * Cfg::kPeers);
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], (PAIR ? 2 : 1) * 4 * EW); }
         fence_barrier_init();
-        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w);
+        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dz);
     }
     if (HAS_BIAS) {
         for (int i = threadIdx.x; i < BN; i += Cfg::kThreads) sBias[i] = (i < ncols) ? a.bias[n0 + i] : 0.f;
     }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
     tc_fence_before_sync();
-    __syncthreads();
+    if (PAIR) cluster_sync_(); else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_slot;
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0 && ncols > 0) {
+        // (issue loops run warp-converged with one elected lane issuing, see the MMA issuer below)
+        if (ncols > 0) {
             uint32_t it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
                     uint8_t* st = smem + s * Cfg::kStageBytes;
-                    tma_load_2d(st, &tm_x, &full[s], kb * BK, tile * BM);
-                    tma_load_2d(st + kABytes, &tm_w, &full[s], kb * BK, n0);
+                    if (elect_one()) {
+                        if (PAIR) {
+                            // both CTAs' bytes are counted on the leader's barrier (the MMA issuer waits there)
+                            if (cr == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+                            tma_load_2d_2sm(st, &tm_x, &full[s], kb * BK, tile * TM + cr * BM);
+                            tma_load_2d_2sm(st + kABytes, &tm_w, &full[s], kb * BK, n0 + cr * (ncolsN >> 1));
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                            tma_load_2d(st, &tm_x, &full[s], kb * BK, tile * BM);
+                            tma_load_2d(st + kABytes, &tm_w, &full[s], kb * BK, n0);
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------
-        if (lane == 0 && ncols > 0) {
-            const uint32_t idesc = make_idesc_bf16(BM, ncols16, false, false);
+        // The whole warp runs the issue loop converged and ONE elected lane issues.  With the loop inside an
+        // `if (lane == 0)` region ptxas keeps the descriptors in vector registers and moves five of them to uniform
+        // registers (ELECT + R2UR.BROADCAST) before every MMA: 143..182 cycles per MMA measured, more than the
+        // 128 cycles the tensor pipe needs (tools/mma_rate_probe.cu).
+        if (ncols > 0 && cr == 0) {
+            const uint32_t idesc = make_idesc_bf16(TM, ncolsN, false, false);
             uint32_t it = 0, tc = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tc) {
                 const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
                 mbar_wait(&t_empty[buf], tph ^ 1);
                 tc_fence_after_sync();
-                if (a.trace && tc < 4) a.trace[blockIdx.x * 64 + tc * 8 + 0] = gtime();
+                if (a.trace && tc < 4 && lane == 0) { a.trace[blockIdx.x * 64 + tc * 8 + 0] = gtime(); a.trace[blockIdx.x * 64 + tc * 8 + 7] = clock64(); }
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after_sync();
-                    if (a.trace && tc < 4 && kb == 0) a.trace[blockIdx.x * 64 + tc * 8 + 1] = gtime();
+                    if (a.trace && tc < 4 && kb == 0 && lane == 0) a.trace[blockIdx.x * 64 + tc * 8 + 1] = gtime();
+                    if (a.trace && blockIdx.x == 0 && tc < 4 && kb < 32 && lane == 0) a.trace[256 * 64 + tc * 32 + kb] = clock64();
                     const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-                    const uint32_t b_addr = a_addr + kABytes;
+                    const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_kmajor(a_addr + kABytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tbase + buf * BN, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
-                                  idesc, (kb | k) != 0);
-                    umma_commit(&empty[s]);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 bytes along K = +2 in the descriptor's 16-byte address field
+                            if (PAIR) umma2_bf16(tbase + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            else umma_bf16(tbase + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if (PAIR) umma2_commit_mc(&empty[s]); else umma_commit(&empty[s]);
+                        if (kb == n_kb - 1) { if (PAIR) umma2_commit_mc(&t_full[buf]); else umma_commit(&t_full[buf]); }
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&t_full[buf]);
-                if (a.trace && tc < 4) a.trace[blockIdx.x * 64 + tc * 8 + 2] = gtime();
+                if (a.trace && tc < 4 && lane == 0) a.trace[blockIdx.x * 64 + tc * 8 + 2] = gtime();
             }
         }
-        __syncwarp();
     } else {
         // ------------------------------ epilogue ----------------------------------
         // warp (q, h): TMEM lane quadrant q = warp % 4 (hardware rule), column slice h; one thread per row.
+        // A thread reads its kGroups * 32 logits from TMEM ONCE, keeps them in registers and hands the accumulator back to
+        // the MMA warp at once; everything after that (max, exp, statistics exchange, grad-logits) runs out of registers.
+        // (Three TMEM sweeps with exp(z - max) parked in TMEM made the epilogue, not the MMAs, the pace of the kernel.)
+        constexpr int G = Cfg::kGroups;
         const int q = warp & 3, h = (warp - kEpiWarp0) >> 2;
         const int r_in_tile = q * 32 + lane;
         const float inv_den = (float)(1.0 / a.den[0]);
         const float s_uniform = a.t_uniform * (float)a.C;
-        // this warp's slice of the CTA's columns, in whole 32-column groups
-        const int n32 = (ncols + 31) >> 5, g_per = (n32 + EW - 1) / EW;
-        const int c_lo = h * g_per * 32;
-        int c_hi = (h + 1) * g_per * 32;
-        c_hi = c_hi > ncols ? ncols : c_hi;
-        const bool dz_vec = (lddz % 8 == 0);
+        const int c_base = h * G * 32;                      // this warp's columns: [c_base, c_base + G * 32) of the unit's BN
+        uint8_t* my_stage = sDz + (warp - kEpiWarp0) * 2 * kStageWarpBytes;
+        uint32_t n_stores = 0;
+        const uint32_t ep_base = (CL > 1) ? *a.xch_epoch : 0u;
         double loss_acc = 0.0;
         uint32_t it = 0;
         for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
             const uint32_t buf = it & 1, tph = (it >> 1) & 1;
-            const int row = tile * BM + r_in_tile;
+            const int row = tile * TM + cr * BM + r_in_tile;
             const bool row_ok = row < a.B;
             const int64_t y = row_ok ? a.y[row] : -1;
             RowMode rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, s_uniform);
             if (!row_ok) { rm.mode = kRowIgnored; rm.omega = 0.f; }
-            const int y_local = (y >= n0 + c_lo && y < n0 + c_hi) ? (int)(y - n0) : -1;   // label column, if in my slice
+            int c_end = c_base + G * 32;
+            c_end = c_end > ncols ? ncols : c_end;
+            const int y_local = (y >= n0 + c_base && y < n0 + c_end) ? (int)(y - n0) : -1;   // label column, if in my slice
             if (ncols > 0) {
-                mbar_wait(&t_full[buf], tph);
+                mbar_wait_warp(&t_full[buf], tph);
                 tc_fence_after_sync();
             }
             const bool tr = a.trace && it < 4 && threadIdx.x == kEpiWarp0 * 32;
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 3] = gtime();
             const uint32_t t_row = tmem_addr(tbase, q * 32, buf * BN);
 
-            // ---- sweep 0: row max (and arg-max / valid-column max) over my slice; no transcendental ----
+            // ---- the one TMEM sweep; the accumulator buffer goes back to the MMA warp right after it ----
+            uint32_t v[G][32];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (c_base + g * 32 < ncols) tmem_ld32(t_row + c_base + g * 32, v[g]);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(&t_empty[buf]); else mbar_arrive(&t_empty[buf]); }
+
+            // ---- row max (and arg-max / valid-column max) over my slice; no transcendental ----
             float m = -INFINITY, mv = -INFINITY;
             int am = 0x7fffffff;
-            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(t_row + c0, v);
-                tmem_ld_wait();
-                float z[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    z[i] = __uint_as_float(v[i]);
-                    if (HAS_BIAS) z[i] += sBias[c0 + i];
-                }
-                if (c0 + 32 > ncols) {
+            for (int g = 0; g < G; ++g) {
+                const int c0 = c_base + g * 32;
+                if (c0 < ncols) {
+                    if (HAS_BIAS || c0 + 32 > ncols) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (c0 + i >= ncols) z[i] = -INFINITY;
-                }
-                const float gm = max32(z);
-                if (WANT_PRED) {
-                    if (gm > m) {                       // first arg-max (numpy tie rule): groups ascend, strict '>'
+                        for (int i = 0; i < 32; ++i) {
+                            float z = __uint_as_float(v[g][i]);
+                            if (HAS_BIAS) z += sBias[c0 + i];
+                            if (c0 + i >= ncols) z = -INFINITY;
+                            v[g][i] = __float_as_uint(z);
+                        }
+                    }
+                    const float gm = max32(v[g]);
+                    if (WANT_PRED) {
+                        if (gm > m) {                       // first arg-max (numpy tie rule): groups ascend, strict '>'
 #pragma unroll
-                        for (int i = 31; i >= 0; --i) if (z[i] == gm) am = n0 + c0 + i;
+                            for (int i = 31; i >= 0; --i) if (__uint_as_float(v[g][i]) == gm) am = n0 + c0 + i;
+                        }
+                    }
+                    m = fmaxf(m, gm);
+                    const int gcol = n0 + c0;
+                    if (gcol + 32 <= a.valid_cols) mv = fmaxf(mv, gm);
+                    else if (gcol < a.valid_cols) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (gcol + i < a.valid_cols) mv = fmaxf(mv, __uint_as_float(v[g][i]));
                     }
                 }
-                m = fmaxf(m, gm);
-                const int gcol = n0 + c0;
-                if (gcol + 32 <= a.valid_cols) mv = fmaxf(mv, gm);
-                else if (gcol < a.valid_cols) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (gcol + i < a.valid_cols) mv = fmaxf(mv, z[i]);
-                }
             }
-            // ---- sweep 1: e = exp(z - m_slice) written back to TMEM; partial sums with 4-way ILP ----
+            // ---- e = exp(z - m_slice) in place; partial sums with 4-way ILP.  The label's logit comes out of a select
+            //      tree and the sum of the logits (uniform-target rows) runs unconditionally: per-element predicates cost
+            //      more instructions than the arithmetic they guard. ----
             float s = 0.f, sumz = 0.f, zy = 0.f;
             {
                 const float mb = m * kLog2e;
                 float s4[4] = {0.f, 0.f, 0.f, 0.f}, z4[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(t_row + c0, v);
-                    tmem_ld_wait();
-                    const bool tail = c0 + 32 > ncols;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float z = __uint_as_float(v[i]);
-                        if (HAS_BIAS) z += sBias[c0 + i];
-                        if (tail && c0 + i >= ncols) z = -INFINITY;
-                        if (i == y_local - c0) zy = z;
-                        if (rm.mode == kRowUniform) z4[i & 3] += (tail && c0 + i >= ncols) ? 0.f : z;
-                        const float e = fast_exp2(fmaf(z, kLog2e, -mb));
-                        s4[i & 3] += e;
-                        v[i] = __float_as_uint(e);
+                for (int g = 0; g < G; ++g) {
+                    const int c0 = c_base + g * 32;
+                    if (c0 < ncols) {
+                        const int yl = y_local - c0;
+                        const float zsel = select32(v[g], yl & 31);
+                        if (yl >= 0 && yl < 32) zy = zsel;
+                        if (c0 + 32 > ncols) {          // tail group: masked columns hold -inf and must not enter the sum
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (c0 + i < ncols) z4[i & 3] += __uint_as_float(v[g][i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) z4[i & 3] += __uint_as_float(v[g][i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float e = fast_exp2(fmaf(__uint_as_float(v[g][i]), kLog2e, -mb));
+                            s4[i & 3] += e;
+                            v[g][i] = __float_as_uint(e);
+                        }
                     }
-                    if (a.write_dz) tmem_st32(t_row + c0, v);
                 }
                 s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
                 sumz = (z4[0] + z4[1]) + (z4[2] + z4[3]);
-                if (a.write_dz) tmem_st_wait();
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 4] = gtime();
-            const float m_slice = m;
-            // ---- combine the column slices of this CTA (shared memory), then the CTAs of the cluster (DSMEM) ----
+            const float m_slice = m, zy_own = zy;
+            // ---- combine the column slices of this CTA (shared memory), then the units of the group (L2) ----
             {
                 float* lx = sLx + (((it & 1) * EW + h) * BM + r_in_tile) * kStatFloats;
                 lx[0] = m; lx[1] = s; lx[2] = zy; lx[3] = sumz; lx[4] = mv; lx[5] = __int_as_float(am);
@@ -365,96 +436,140 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     zy += o[2]; sumz += o[3];
                 }
             }
+            const float m_cta = m;              // max over this unit's columns (for the arg-max fold at the end)
             if (CL > 1) {
-                // Through L2, not DSMEM: with the tensor pipe busy on the next tile, remote shared-memory stores
-                // and arrives to a peer SM took ~8 us per tile (measured); a global round trip takes ~1.5 us.
-                const uint32_t par = it & 1;
-                float* xs = a.xch_stats + ((size_t)(cluster_id * 2 + par) * CL) * BM * kStatFloats;
-                unsigned int* xf = a.xch_flags + (size_t)(cluster_id * 2 + par) * CL * 4;
+                // Through L2, not DSMEM: with the tensor pipe busy on the next tile, remote shared-memory stores and
+                // arrives to a peer SM took ~8 us per tile (measured).  One thread per row publishes (value, epoch)
+                // words and polls the peers' words of the same row: one L2 round trip, no flag, no fence.  Everybody
+                // needs the row max and sum of the whole head now; the other four statistics only feed the per-row
+                // outputs, which unit 0 collects AFTER the grad-logits are out (registers are free again by then).
+                float* sg = sG + ((it & 1) * BM + r_in_tile) * 2;
                 if (h == 0) {
-                    float2* dst = reinterpret_cast<float2*>(xs + ((size_t)rank * BM + r_in_tile) * kStatFloats);
-                    __stcg(dst + 0, make_float2(m, s)); __stcg(dst + 1, make_float2(zy, sumz));
-                    __stcg(dst + 2, make_float2(mv, __int_as_float(am)));
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) st_release_gpu(xf + rank * 4 + q, it + 1);
-                }
-                if (lane < CL && lane != (int)rank) {
-                    while (ld_acquire_gpu(xf + lane * 4 + q) < it + 1) { }
-                }
-                __syncwarp();
-                float mg = m;
-                float2 pv[Cfg::kPeers][3];
+                    const uint32_t ep = ep_base + it + 1;
+                    uint2* xs = a.xch_stats + ((size_t)(xid * 2 + (it & 1)) * CL) * BM * kStatFloats;
+                    uint2* dst = xs + ((size_t)rank * BM + r_in_tile) * kStatFloats;
+                    st_ll(dst + 0, m, ep); st_ll(dst + 1, s, ep);
+                    if (rank != 0) {
+                        st_ll(dst + 2, zy, ep); st_ll(dst + 3, sumz, ep); st_ll(dst + 4, mv, ep); st_ll(dst + 5, __int_as_float(am), ep);
+                    }
+                    uint2 pv[Cfg::kPeers][2];
+                    bool ok;
+                    do {
+                        ok = true;
 #pragma unroll
-                for (int d = 1; d < CL; ++d) {
-                    const uint32_t peer = (rank + d) % CL;
-                    const float2* src = reinterpret_cast<const float2*>(xs + ((size_t)peer * BM + r_in_tile) * kStatFloats);
-                    pv[d - 1][0] = __ldcg(src); pv[d - 1][1] = __ldcg(src + 1); pv[d - 1][2] = __ldcg(src + 2);
-                    mg = fmaxf(mg, pv[d - 1][0].x);
-                }
-                s *= fast_exp2((m - mg) * kLog2e);
-                // ties between CTAs resolve to the smaller column index, i.e. scan peers in rank order
+                        for (int d = 1; d < CL; ++d) {
+                            const uint2* src = xs + ((size_t)((rank + d) % CL) * BM + r_in_tile) * kStatFloats;
+                            pv[d - 1][0] = ld_ll(src); pv[d - 1][1] = ld_ll(src + 1);
+                        }
 #pragma unroll
-                for (int d = 1; d < CL; ++d) {
-                    const float pm = pv[d - 1][0].x;
-                    const int pam = __float_as_int(pv[d - 1][2].y);
-                    s += pv[d - 1][0].y * fast_exp2((pm - mg) * kLog2e);
-                    if (pm > m || (pm == m && pam < am)) { am = pam; m = pm; }
-                    zy += pv[d - 1][1].x; sumz += pv[d - 1][1].y; mv = fmaxf(mv, pv[d - 1][2].x);
+                        for (int d = 1; d < CL; ++d) ok = ok && (pv[d - 1][0].y == ep) && (pv[d - 1][1].y == ep);
+                    } while (!ok);
+                    float mg = m;
+#pragma unroll
+                    for (int d = 1; d < CL; ++d) mg = fmaxf(mg, __uint_as_float(pv[d - 1][0].x));
+                    s *= fast_exp2((m - mg) * kLog2e);
+#pragma unroll
+                    for (int d = 1; d < CL; ++d)
+                        s += __uint_as_float(pv[d - 1][1].x) * fast_exp2((__uint_as_float(pv[d - 1][0].x) - mg) * kLog2e);
+                    m = mg;
+                    sg[0] = m; sg[1] = s;
                 }
-                m = mg;
+                asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
+                if (h != 0) { m = sg[0]; s = sg[1]; }
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 5] = gtime();
-            const float lse = m + fast_log2(s) * kLn2;
-            const bool is_col = (y >= 0 && y < a.C);
-            if (rank == 0 && h == 0 && row_ok) {
-                float rowloss = 0.f;
-                if (rm.mode == kRowOneHot) rowloss = rm.omega * (lse - zy);
-                else if (rm.mode == kRowUniform) rowloss = a.t_uniform * ((float)a.C * lse - sumz);
-                else if (rm.mode == kRowBad) rowloss = __int_as_float(0x7fc00000);
-                loss_acc += (double)rowloss;
-                if (a.row_ptgt) a.row_ptgt[row] = is_col ? fast_exp2((zy - lse) * kLog2e) : 0.f;
-                if (a.row_pmax) a.row_pmax[row] = fast_exp2((mv - lse) * kLog2e);
-                if (WANT_PRED) {
-                    if (a.row_pmax_all) a.row_pmax_all[row] = fast_exp2((m - lse) * kLog2e);
-                    if (a.row_pred) a.row_pred[row] = am;
-                }
-            }
-            // ---- sweep 2: un-scaled grad-logits  dz = (S p - T) / den = coef * e - T/den  -> bf16 -> global ----
+            // ---- un-scaled grad-logits  dz = (S p - T) / den = coef * e - T/den  -> bf16 -> swizzled smem -> TMA store ----
+            // (a thread owns a row, so direct stores would scatter 16-byte pieces over 32 rows per instruction; the TMA
+            // store writes whole 128-byte lines and clips the columns >= C and the rows >= B itself)
             if (a.write_dz) {
                 const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
                 const float coef = live ? inv_den * rm.omega / s : 0.f;
                 const float coef_e = coef * fast_exp2((m_slice - m) * kLog2e);   // e was taken relative to the slice max
                 const float t_all = (rm.mode == kRowUniform) ? inv_den * a.t_uniform : 0.f;
                 const float t_hot = (rm.mode == kRowOneHot) ? inv_den * rm.omega : 0.f;
-                const float gy = fmaf(coef, fast_exp2((zy - m) * kLog2e), -t_all) - t_hot;   // label column
-                __nv_bfloat16* drow = dz + (int64_t)row * lddz + n0;
-                for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(t_row + c0, v);
-                    tmem_ld_wait();
-                    float g[32];
+                const float gy = fmaf(coef, fast_exp2((zy_own - m) * kLog2e), -t_all) - t_hot;   // label column
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        g[i] = fmaf(coef_e, __uint_as_float(v[i]), -t_all);
-                        if (i == y_local - c0) g[i] = gy;
-                    }
-                    if (row_ok) {
-                        if (dz_vec && c0 + 32 <= ncols) {
+                for (int b = 0; b < (G + 1) / 2; ++b) {         // boxes of 64 columns
+                    const int c0 = c_base + b * 64;
+                    if (c0 < ncols) {
+                        uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
+                        if (lane == 0) tma_store_wait_read<1>();        // the store that read this buffer two boxes ago is done
+                        __syncwarp();
 #pragma unroll
-                            for (int cch = 0; cch < 4; ++cch) store8_bf16(drow + c0 + cch * 8, g + cch * 8);
-                        } else {
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int g = 2 * b + hh;
+                            if (g < G && c0 + hh * 32 < ncols) {
+                                float gl[32];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) if (c0 + i < ncols) drow[c0 + i] = __float2bfloat16_rn(g[i]);
+                                for (int i = 0; i < 32; ++i) gl[i] = fmaf(coef_e, __uint_as_float(v[g < G ? g : 0][i]), -t_all);
+#pragma unroll
+                                for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, hh * 4 + cch, gl + cch * 8);
+                            }
                         }
+                        // the label column carries the -T term of a one-hot row: patched in the staged row by its owner
+                        const int cl = y_local - c0;
+                        if (y_local >= 0 && cl >= 0 && cl < 64)
+                            *reinterpret_cast<__nv_bfloat16*>(sbuf + lane * 128 + (((cl >> 3) ^ (lane & 7)) << 4) + (cl & 7) * 2) = __float2bfloat16_rn(gy);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tm_dz, sbuf, n0 + c0, tile * TM + cr * BM + q * 32);
+                            tma_store_commit();
+                        }
+                        ++n_stores;
+                    }
+                }
+            }
+            // ---- per-row outputs (unit 0 of the group): loss, p[target], max p over the valid columns, max p, arg-max ----
+            if (rank == 0 && h == 0) {
+                if (CL > 1) {
+                    const uint32_t ep = ep_base + it + 1;
+                    const uint2* xs = a.xch_stats + ((size_t)(xid * 2 + (it & 1)) * CL) * BM * kStatFloats;
+                    // all peers' words in flight at once (one L2 round trip; the logits' registers are free again)
+                    uint2 w[Cfg::kPeers][kStatFloats];
+                    bool ok;
+                    do {
+                        ok = true;
+#pragma unroll
+                        for (int d = 1; d < CL; ++d) {
+                            const uint2* src = xs + ((size_t)d * BM + r_in_tile) * kStatFloats;
+#pragma unroll
+                            for (int j = 0; j < kStatFloats; ++j) if (j != 1) w[d - 1][j] = ld_ll(src + j);
+                        }
+#pragma unroll
+                        for (int d = 1; d < CL; ++d)
+#pragma unroll
+                            for (int j = 0; j < kStatFloats; ++j) if (j != 1) ok = ok && (w[d - 1][j].y == ep);
+                    } while (!ok);
+                    float m_am = m_cta;
+#pragma unroll
+                    for (int d = 1; d < CL; ++d) {          // units in column order, so ties keep the smaller column index
+                        const float pm = __uint_as_float(w[d - 1][0].x);
+                        const int pam = (int)w[d - 1][5].x;
+                        if (pm > m_am || (pm == m_am && pam < am)) { am = pam; m_am = pm; }
+                        zy += __uint_as_float(w[d - 1][2].x); sumz += __uint_as_float(w[d - 1][3].x);
+                        mv = fmaxf(mv, __uint_as_float(w[d - 1][4].x));
+                    }
+                }
+                if (row_ok) {
+                    const float lse = m + fast_log2(s) * kLn2;
+                    const bool is_col = (y >= 0 && y < a.C);
+                    float rowloss = 0.f;
+                    if (rm.mode == kRowOneHot) rowloss = rm.omega * (lse - zy);
+                    else if (rm.mode == kRowUniform) rowloss = a.t_uniform * ((float)a.C * lse - sumz);
+                    else if (rm.mode == kRowBad) rowloss = __int_as_float(0x7fc00000);
+                    loss_acc += (double)rowloss;
+                    if (a.row_ptgt) a.row_ptgt[row] = is_col ? fast_exp2((zy - lse) * kLog2e) : 0.f;
+                    if (a.row_pmax) a.row_pmax[row] = fast_exp2((mv - lse) * kLog2e);
+                    if (WANT_PRED) {
+                        if (a.row_pmax_all) a.row_pmax_all[row] = fast_exp2((m - lse) * kLog2e);
+                        if (a.row_pred) a.row_pred[row] = am;
                     }
                 }
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 6] = gtime();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
+        if (lane == 0) tma_store_wait<0>();
         // ---- deterministic loss reduction: quadrants in order, CTAs in order ----
         __shared__ double s_loss[4];
         double wl = warp_sum(loss_acc);
@@ -471,13 +586,13 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 a.loss_num[0] = tot;
                 a.loss[0] = (float)(tot / a.den[0]);
                 *a.ticket = 0u;
+                if (CL > 1) *a.xch_epoch = ep_base + (uint32_t)((n_tiles + n_clusters - 1) / n_clusters) + 1u;
             }
         }
     }
     tc_fence_before_sync();
-    __syncthreads();
-    if (CL > 1 && threadIdx.x < 8) a.xch_flags[((size_t)(cluster_id * 2 + (threadIdx.x >> 2)) * CL + rank) * 4 + (threadIdx.x & 3)] = 0u;
-    if (warp == 1) tmem_dealloc(tbase, Cfg::kTmemCols);
+    if (PAIR) cluster_sync_(); else __syncthreads();
+    if (warp == 1) { if (PAIR) tmem_dealloc2(tbase, Cfg::kTmemCols); else tmem_dealloc(tbase, Cfg::kTmemCols); }
 }
 
 // =================================================================================================
@@ -517,49 +632,50 @@ head_dx_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     const int total = m_tiles * n_tiles;
     const int n_kb = (C + BK - 1) / BK;
 
+    // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int mt = tile / n_tiles, nt = tile % n_tiles;
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * kDxStageBytes;
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full[s], kDxStageBytes);
-                    uint8_t* st = smem + s * kDxStageBytes;
                     tma_load_2d(st, &tm_dz, &full[s], kb * BK, mt * BM);                        // 64 classes x 128 rows
 #pragma unroll
                     for (int j = 0; j < 4; ++j)                                                  // 64 features x 64 classes
                         tma_load_2d(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + j * 64, kb * BK);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BM, kDxBN, false, true);
-            uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
-                const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-                mbar_wait(&t_empty[buf], tph ^ 1);
+        const uint32_t idesc = make_idesc_bf16(BM, kDxBN, false, true);
+        uint32_t it = 0, tc = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+            const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+            mbar_wait(&t_empty[buf], tph ^ 1);
+            tc_fence_after_sync();
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
+                mbar_wait(&full[s], ph);
                 tc_fence_after_sync();
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(smem + s * kDxStageBytes);
-                    const uint32_t b_addr = a_addr + kABytes;
-                    const int rem = C - kb * BK;
-                    const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(tbase + buf * kDxBN, make_desc_kmajor(a_addr + k * 32),
-                                  make_desc_mnmajor(b_addr + k * 2048, kBoxBytes), idesc, (kb | k) != 0);
+                const uint32_t a_addr = smem_u32(smem + s * kDxStageBytes);
+                const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_mnmajor(a_addr + kABytes, kBoxBytes);
+                const int rem = C - kb * BK;
+                const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)        // +32 B (K-major) / +2048 B (MN-major) per 16 K, in 16-byte units
+                        if (k < ksteps) umma_bf16(tbase + buf * kDxBN, adesc + 2 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
                     umma_commit(&empty[s]);
+                    if (kb == n_kb - 1) umma_commit(&t_full[buf]);
                 }
-                umma_commit(&t_full[buf]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         const int q = warp & 3;
         uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
@@ -611,16 +727,20 @@ head_dx_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
 // CTA r of the pair loads rows [128 r, +128) of the dZ tile and features [128 r, +128) of the W tile (32 KB per stage
 // instead of 48 KB), the leader issues the MMAs, each CTA drains its own 128 x 256 accumulator from its TMEM.
 // =================================================================================================
-constexpr int kDx2Stages = 6;
+// kDx2EW warps per TMEM lane quadrant drain the accumulator.
+constexpr int kDx2EW = 2;
+constexpr int kDx2Threads = (2 + 4 * kDx2EW) * 32;
+constexpr int kDx2Stages = 5;
 constexpr int kDx2StageBytes = kABytes + 2 * kBoxBytes;         // 32 KB per CTA
 constexpr int kDx2OffStage = kDx2Stages * kDx2StageBytes;
-constexpr int kDx2OffBars = kDx2OffStage + 4 * 2 * kStageWarpBytes;
+constexpr int kDx2OffBars = kDx2OffStage + 4 * (kDxBN / 64) * kStageWarpBytes;      // one staging buffer per (quadrant, 64-column box)
 constexpr int kDx2SmemBytes = kDx2OffBars + (2 * kDx2Stages + 4) * 8 + 16 + 1024;
 static_assert(kDx2SmemBytes <= 232448, "dx2 kernel shared memory");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDx2Threads, 1)
 head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_w,
-                const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, const float* __restrict__ gscale) {
+                const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, const float* __restrict__ gscale,
+                long long* trace, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sStage = smem + kDx2OffStage;
@@ -633,7 +753,7 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kDx2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }     // 4 epilogue warps x 2 CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 2 * 4 * kDx2EW); }     // epilogue warps x 2 CTAs
         fence_barrier_init();
         prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dx);
     }
@@ -647,86 +767,111 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     const int n_kb = (C + BK - 1) / BK;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = pair; tile < total; tile += n_pairs) {
-                const int mt = tile / n_tiles, nt = tile % n_tiles;
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDx2StageBytes);     // both CTAs' bytes land on the leader's barrier
-                    uint8_t* st = smem + s * kDx2StageBytes;
-                    tma_load_2d_2sm(st, &tm_dz, &full[s], kb * BK, mt * 256 + rank * 128);               // 64 classes x 128 rows
+        uint32_t it = 0;
+        for (int tile = pair; tile < total; tile += n_pairs) {
+            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * kDx2StageBytes;
+                if (elect_one()) {
+                    if ((dbg & 1) && it >= kDx2Stages) {        // developer probe: MMA rate without operand traffic (stale tiles)
+                        if (rank == 0) mbar_arrive(&full[s]);
+                    } else {
+                        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDx2StageBytes);     // both CTAs' bytes land on the leader's barrier
+                        tma_load_2d_2sm(st, &tm_dz, &full[s], kb * BK, mt * 256 + rank * 128);               // 64 classes x 128 rows
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)                                                         // 64 features x 64 classes
-                        tma_load_2d_2sm(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kb * BK);
+                        for (int j = 0; j < 2; ++j)                                                         // 64 features x 64 classes
+                            tma_load_2d_2sm(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kb * BK);
+                    }
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             const uint32_t idesc = make_idesc_bf16(256, kDxBN, false, true);
             uint32_t it = 0, tc = 0;
             for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
                 const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
                 mbar_wait(&t_empty[buf], tph ^ 1);
                 tc_fence_after_sync();
+                if (trace && tc < 8 && lane == 0) { trace[blockIdx.x * 64 + tc * 8 + 0] = gtime(); trace[blockIdx.x * 64 + tc * 8 + 7] = clock64(); }
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after_sync();
+                    if (trace && blockIdx.x == 0 && tc >= 1 && tc < 3 && lane == 0) trace[256 * 64 + (tc - 1) * 32 + kb] = clock64();
                     const uint32_t a_addr = smem_u32(smem + s * kDx2StageBytes);
-                    const uint32_t b_addr = a_addr + kABytes;
+                    const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_mnmajor(a_addr + kABytes, kBoxBytes);
                     const int rem = C - kb * BK;
                     const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
-                    for (int k = 0; k < ksteps; ++k)
-                        umma2_bf16(tbase + buf * kDxBN, make_desc_kmajor(a_addr + k * 32),
-                                   make_desc_mnmajor(b_addr + k * 2048, kBoxBytes), idesc, (kb | k) != 0);
-                    umma2_commit_mc(&empty[s]);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            if (k < ksteps) umma2_bf16(tbase + buf * kDxBN, adesc + 2 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
+                        umma2_commit_mc(&empty[s]);
+                        if (kb == n_kb - 1) umma2_commit_mc(&t_full[buf]);
+                    }
+                    __syncwarp();
                 }
-                umma2_commit_mc(&t_full[buf]);
+                if (trace && tc < 8 && lane == 0) trace[blockIdx.x * 64 + tc * 8 + 2] = gtime();
             }
         }
         __syncwarp();
     } else {
-        const int q = warp & 3;
-        uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
+        // warp (q, hh): lane quadrant q, column half hh.  A thread pulls its 128 accumulator columns into registers with one
+        // TMEM sweep and hands the buffer back to the MMA warp at once; conversion, staging and the TMA stores run after
+        // that.  Every 64-column box has its own staging buffer, so nothing waits for a store issued in the same tile
+        // (with two buffers per warp and four boxes per tile the drain waited ~0.5 us per box for the store two boxes
+        // back to finish reading, 4.5 us per tile against 5.3 us of MMAs).
+        const int q = warp & 3, hh = (warp - kEpiWarp0) >> 2;
+        constexpr int kBoxes = kDxBN / 64 / kDx2EW;                  // boxes (and staging buffers) per warp
+        uint8_t* my_stage = sStage + (hh * 4 + q) * kBoxes * kStageWarpBytes;
         const float gs = gscale ? gscale[0] : 1.f;
-        uint32_t tc = 0, n_stores = 0;
+        uint32_t tc = 0;
         for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
             const int mt = tile / n_tiles, nt = tile % n_tiles;
             const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-            mbar_wait(&t_full[buf], tph);
+            mbar_wait_warp(&t_full[buf], tph);
             tc_fence_after_sync();
-            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kDxBN; c0 += 64) {
-                uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
+            const bool tr = trace && tc < 8 && threadIdx.x == kEpiWarp0 * 32;
+            if (tr) trace[blockIdx.x * 64 + tc * 8 + 3] = gtime();
+            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN + hh * kBoxes * 64);
+            uint32_t v[2 * kBoxes][32];
+            if (!(dbg & 2)) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
-                    tmem_ld32(t_row + c0 + h * 32, v);
-                    tmem_ld_wait();
-                    float g[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[i]);
-#pragma unroll
-                    for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tm_dx, sbuf, nt * kDxBN + c0, mt * 256 + rank * 128 + q * 32);
-                    tma_store_commit();
-                }
-                ++n_stores;
+                for (int g = 0; g < 2 * kBoxes; ++g) tmem_ld32(t_row + g * 32, v[g]);
+                tmem_ld_wait();
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&t_empty[buf]);
+            if (lane == 0) {
+                mbar_arrive_leader(&t_empty[buf]);
+                tma_store_wait_read<0>();                            // last tile's stores have read the staging buffers
+            }
+            __syncwarp();
+            if (!(dbg & 2)) {
+#pragma unroll
+                for (int b = 0; b < kBoxes; ++b) {
+                    uint8_t* sbuf = my_stage + b * kStageWarpBytes;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float g[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[2 * b + h][i]);
+#pragma unroll
+                        for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_dx, sbuf, nt * kDxBN + (hh * kBoxes + b) * 64, mt * 256 + rank * 128 + q * 32);
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (tr) trace[blockIdx.x * 64 + tc * 8 + 4] = gtime();
         }
         if (lane == 0) tma_store_wait<0>();
     }
@@ -771,40 +916,39 @@ head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     const int kb_total = (B + BK - 1) / BK;
     const int kb0 = (int)((int64_t)kb_total * sp / splits), kb1 = (int)((int64_t)kb_total * (sp + 1) / splits);
 
+    // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
+        uint32_t it = 0;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * kDwStageBytes;
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], kDwStageBytes);
-                uint8_t* st = smem + s * kDwStageBytes;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) tma_load_2d(st + j * kBoxBytes, &tm_dz, &full[s], mt * BM + j * 64, kb * BK);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tma_load_2d(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + j * 64, kb * BK);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BM, kDwBN, true, true);
-            uint32_t it = 0;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
-                mbar_wait(&full[s], ph);
-                tc_fence_after_sync();
-                const uint32_t a_addr = smem_u32(smem + s * kDwStageBytes);
-                const uint32_t b_addr = a_addr + 2 * kBoxBytes;
+        const uint32_t idesc = make_idesc_bf16(BM, kDwBN, true, true);
+        uint32_t it = 0;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32(smem + s * kDwStageBytes);
+            const uint64_t adesc = make_desc_mnmajor(a_addr, kBoxBytes), bdesc = make_desc_mnmajor(a_addr + 2 * kBoxBytes, kBoxBytes);
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    umma_bf16(tbase, make_desc_mnmajor(a_addr + k * 2048, kBoxBytes),
-                              make_desc_mnmajor(b_addr + k * 2048, kBoxBytes), idesc, (it | k) != 0);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tbase, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
                 umma_commit(&empty[s]);
+                if (kb == kb1 - 1) umma_commit(t_full);
             }
-            umma_commit(t_full);
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         const int q = warp & 3;
         const int cls = mt * BM + q * 32 + lane;
@@ -892,43 +1036,52 @@ static int set_smem(KernelT kernel, int bytes) {
     return OSB_OK;
 }
 
-template <int BN, int CL, int STAGES, int EW, bool HAS_BIAS, bool WANT_PRED>
-static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, __nv_bfloat16* dz, int64_t lddz, const FwdArgs& a,
+template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED>
+static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
                         cudaStream_t st) {
-    using Cfg = FwdCfg<BN, CL, STAGES, EW>;
-    const int n_tiles = (a.B + BM - 1) / BM;
-    auto k = head_fwd_kernel<BN, CL, STAGES, EW, HAS_BIAS, WANT_PRED>;
+    using Cfg = FwdCfg<BN, CL, STAGES, EW, PAIR>;
+    constexpr int kCtasPerGroup = CL * (PAIR ? 2 : 1);
+    const int n_tiles = (a.B + Cfg::kTileRows - 1) / Cfg::kTileRows;
+    auto k = head_fwd_kernel<BN, CL, STAGES, EW, PAIR, HAS_BIAS, WANT_PRED>;
     int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(sm_count() / CL * CL);
     cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    // persistent kernel, one CTA per SM, launched cooperatively when CTAs wait on each other (CL > 1): every CTA of a
+    // persistent kernel, one CTA per SM, launched cooperatively when units wait on each other (CL > 1): every CTA of a
     // group must be resident while its peers spin on its statistics flags
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = CL > 1 ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int groups = cta_limit() / CL;
-    if (groups > n_tiles) groups = n_tiles;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
+    if (PAIR) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    int groups = cta_limit() / kCtasPerGroup;
+    if (groups * (PAIR ? 2 : 1) > kMaxXid) groups = kMaxXid / (PAIR ? 2 : 1);
     if (groups < 1) groups = 1;
-    cfg.gridDim = dim3(groups * CL);
-    OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, dz, lddz, a));
+    // every group runs ceil(n_tiles / groups) rounds: use the fewest groups that keep that round count (the others
+    // would only add L2 traffic contention and power)
+    const int rounds = (n_tiles + groups - 1) / groups;
+    groups = (n_tiles + rounds - 1) / rounds;
+    cfg.gridDim = dim3(groups * kCtasPerGroup);
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a));
     return OSB_OK;
 }
 
-template <int BN, int CL, int STAGES, int EW>
-static int launch_fwd(const CUtensorMap& tx, const CUtensorMap& tw, __nv_bfloat16* dz, int64_t lddz, const FwdArgs& a,
+template <int BN, int CL, int STAGES, int EW, bool PAIR>
+static int launch_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
                       cudaStream_t st) {
     const bool pred = a.row_pred || a.row_pmax_all;
-    if (a.bias) return pred ? launch_fwd_k<BN, CL, STAGES, EW, true, true>(tx, tw, dz, lddz, a, st)
-                            : launch_fwd_k<BN, CL, STAGES, EW, true, false>(tx, tw, dz, lddz, a, st);
-    return pred ? launch_fwd_k<BN, CL, STAGES, EW, false, true>(tx, tw, dz, lddz, a, st)
-                : launch_fwd_k<BN, CL, STAGES, EW, false, false>(tx, tw, dz, lddz, a, st);
+    if (a.bias) return pred ? launch_fwd_k<BN, CL, STAGES, EW, PAIR, true, true>(tx, tw, tdz, a, st)
+                            : launch_fwd_k<BN, CL, STAGES, EW, PAIR, true, false>(tx, tw, tdz, a, st);
+    return pred ? launch_fwd_k<BN, CL, STAGES, EW, PAIR, false, true>(tx, tw, tdz, a, st)
+                : launch_fwd_k<BN, CL, STAGES, EW, PAIR, false, false>(tx, tw, tdz, a, st);
 }
 
-static int fwd_box_rows(int C) { return C <= 128 ? 128 : 256; }
+// rows of the W box one CTA stages per k-block
+static int fwd_box_rows(int C, bool pair) { return (C <= 128 ? 128 : 256) / (pair ? 2 : 1); }
 
 }  // namespace head
 }  // namespace osb
@@ -941,6 +1094,8 @@ static int g_head_pairs = 1;          // 1: GEMMs run on CTA pairs (cta_group::2
 extern "C" void osb_debug_set_head_pairs(int on) { g_head_pairs = on; }
 static thread_local bool g_dw_partials_only = false;   // set by osb_head_backward_dw_partials around its call
 static long long* g_trace = nullptr;
+static int g_dbg = 0;
+extern "C" void osb_debug_set_head_dbg(int v) { g_dbg = v; }
 // developer hook (not part of the public header): device buffer of [grid][64] int64 clock stamps, or NULL
 extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<long long*>(p); }
 
@@ -987,8 +1142,10 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tx, tw;
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, BM), "x");
-    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, fwd_box_rows(C)), "w");
-    __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dz);
+    const bool pair = g_head_pairs != 0;
+    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, fwd_box_rows(C, pair)), "w");
+    CUtensorMap tdz = tx;       // placeholder when no grad-logits are written
+    if (dz) OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 32), "dz (store)");
     FwdArgs a;
     a.bias = bias; a.y = y; a.class_w = class_w; a.B = (int)B; a.K = K; a.C = C; a.variant = variant;
     a.t_uniform = (float)(unk_weight / (double)C);
@@ -998,14 +1155,21 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.write_dz = dz ? 1 : 0;
     a.ticket = reinterpret_cast<unsigned int*>(ws);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kWsOffPartials);
-    a.xch_flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffFlags);
-    a.xch_stats = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffStats);
+    a.xch_epoch = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffEpoch);
+    a.xch_stats = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + kWsOffStats);
     a.trace = g_trace;
-    if (C <= 128) return launch_fwd<128, 1, 6, 2>(tx, tw, dzp, lddz, a, st);
-    if (C <= 256) return launch_fwd<256, 1, 4, 2>(tx, tw, dzp, lddz, a, st);
-    if (C <= 512) return launch_fwd<256, 2, 4, 2>(tx, tw, dzp, lddz, a, st);
-    if (C <= 768) return launch_fwd<256, 3, 4, 2>(tx, tw, dzp, lddz, a, st);
-    return launch_fwd<256, 4, 4, 2>(tx, tw, dzp, lddz, a, st);
+    if (pair) {
+        if (C <= 128) return launch_fwd<128, 1, 6, 2, true>(tx, tw, tdz, a, st);
+        if (C <= 256) return launch_fwd<256, 1, 4, 2, true>(tx, tw, tdz, a, st);
+        if (C <= 512) return launch_fwd<256, 2, 4, 2, true>(tx, tw, tdz, a, st);
+        if (C <= 768) return launch_fwd<256, 3, 4, 2, true>(tx, tw, tdz, a, st);
+        return launch_fwd<256, 4, 4, 2, true>(tx, tw, tdz, a, st);
+    }
+    if (C <= 128) return launch_fwd<128, 1, 4, 2, false>(tx, tw, tdz, a, st);
+    if (C <= 256) return launch_fwd<256, 1, 3, 2, false>(tx, tw, tdz, a, st);
+    if (C <= 512) return launch_fwd<256, 2, 3, 2, false>(tx, tw, tdz, a, st);
+    if (C <= 768) return launch_fwd<256, 3, 3, 2, false>(tx, tw, tdz, a, st);
+    return launch_fwd<256, 4, 3, 2, false>(tx, tw, tdz, a, st);
 }
 
 extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
@@ -1034,7 +1198,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
             const int total2 = (int)((B + 255) / 256) * ((K + kDxBN - 1) / kDxBN);
             int pairs = cta_limit() / 2;
             if (pairs > total2) pairs = total2;
-            head_dx2_kernel<<<pairs * 2, kThreads, kDx2SmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
+            head_dx2_kernel<<<pairs * 2, kDx2Threads, kDx2SmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale, g_trace, g_dbg);
             OSB_LAUNCH_CHECK();
         } else {
             rc = set_smem(head_dx_kernel, kDxSmemBytes);

@@ -47,6 +47,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// Whole-warp wait for long waits (an epilogue warp waiting for a tile): ONE lane polls, with a back-off, and the rest
+// of the warp parks on the warp barrier.  128+ threads spinning on try_wait compete with the tensor core's operand
+// reads for shared-memory bandwidth (measured: a k-block of 4 MMAs took 727 cycles instead of 573).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+    }
+    __syncwarp();
+}
 
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {

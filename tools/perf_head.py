@@ -33,7 +33,7 @@ def head_case(B, K, C, variant="entropic"):
     counts = torch.empty(4, dtype=torch.int64, device=dev)
     loss = torch.empty(1, device=dev); num = torch.empty(1, dtype=torch.float64, device=dev)
     stats = torch.empty(3, B, device=dev); pred = torch.empty(B, dtype=torch.int32, device=dev)
-    lddz = (C + 7) // 8 * 8
+    _al = int(os.environ.get("OSB_LDDZ_ALIGN", "8")); lddz = (C + _al - 1) // _al * _al
     dz = torch.empty(B, lddz, dtype=torch.bfloat16, device=dev)
     dx = torch.empty(B, K, dtype=torch.bfloat16, device=dev); dw = torch.empty(C, K, device=dev)
     vnum = {"entropic": 0, "softmax": 1, "garbage": 2}[variant]

@@ -14,6 +14,7 @@ plan = HeadPlan(B, K, C, device=dev)
 lib = L.load()
 lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
 trace = torch.zeros(512, 64, dtype=torch.int64, device=dev)
+if os.environ.get("OSB_PAIRS") == "0": lib.osb_debug_set_head_pairs(0)
 plan.label_stats(y)
 for _ in range(3): plan.forward(x, w, y)
 torch.cuda.synchronize()
@@ -25,7 +26,7 @@ t = trace.cpu().numpy()
 names = ["mma_start", "first_A_full", "mma_issued", "epi_tfull", "sweepA_done", "xchg_done", "sweepB_done"]
 gbase = t[:, 0][t[:, 0] > 0].min()
 nodz = len(sys.argv) > 4
-for cta in (0, 1, 2, 3, 4, 5, 130, 131):
+for cta in (0, 2, 4, 6, 121):
     row = t[cta]
     if row[0] == 0 and row[3] == 0: continue
     base = gbase
@@ -33,3 +34,12 @@ for cta in (0, 1, 2, 3, 4, 5, 130, 131):
         r = row[it * 8: it * 8 + 7]
         if r.max() == 0: continue
         print(f"cta {cta:3d} tile#{it}: " + "  ".join(f"{n}={int(v - base):7d}" for n, v in zip(names, r)))
+
+r = t[0]
+if r[8 * 3 + 7] and r[7]:
+    print(f"SM clock during the launch: {(r[8 * 3 + 7] - r[7]) / max(1, (r[8 * 3] - r[0])) * 1e3:.0f} MHz")
+
+kb = t[256:258].reshape(-1)
+kb = kb[kb > 0]
+if len(kb) > 1:
+    print("cycles between k-block issues (CTA 0, tiles 0-3):", " ".join(str(int(v)) for v in np.diff(kb)))
