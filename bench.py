@@ -161,7 +161,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
             return
         plan.label_stats(y, sp._den_hook)
         ev[0].record()
-        plan.forward(x, w, y)
+        plan.forward(x, w, y, want_pred=False)
         ev[1].record()
         if sp.peer is not None:
             plan.backward_dw_partials(x)

@@ -75,6 +75,15 @@ __device__ __forceinline__ void mbar_arrive_peer(uint32_t raddr) {
 __device__ __forceinline__ void st_ll(uint2* p, float v, uint32_t epoch) {
     asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
+// the same 8-byte words in shared memory, between the two threads that own one row inside a CTA (no CTA barrier)
+__device__ __forceinline__ void sts_ll(uint2* p, float v, uint32_t epoch) {
+    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" :: "r"(osb::tc::smem_u32(p)), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 lds_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(osb::tc::smem_u32(p)) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint2 ld_ll(const uint2* p) {
     uint2 v;
     asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
@@ -138,9 +147,9 @@ struct FwdCfg {
     static constexpr int kTileRows = PAIR ? 2 * BM : BM;                           // rows per tile of a CTA pair / a CTA
     static constexpr int kPeers = CL > 1 ? CL - 1 : 1;
     static constexpr int kOffDz = STAGES * kStageBytes;                            // [4 EW warps][2] boxes of 32 rows x 128 B (grad-logits staging)
-    static constexpr int kOffLx = kOffDz + 4 * EW * 2 * kStageWarpBytes;           // [2][EW][128][6] floats
-    static constexpr int kOffG = kOffLx + 2 * EW * BM * kStatFloats * 4;           // [2][128][2] floats: row max / sum of the whole head
-    static constexpr int kOffBias = kOffG + 2 * BM * 2 * 4;                        // [BN] floats
+    static constexpr int kOffX = kOffDz + 4 * EW * 2 * kStageWarpBytes;            // [2][128][8] (value, epoch) words between the two owners of a row
+    static constexpr int kOffBias = kOffX + 2 * BM * 8 * 8;                        // [BN] floats
+    static_assert(EW == 2, "the epilogue pairs exactly two threads per accumulator row");
     static constexpr int kGroups = BN / 32 / EW;                                   // 32-column groups per epilogue thread
     static constexpr int kOffBars = kOffBias + BN * 4;
     static constexpr int kNumBars = 2 * STAGES + 4;
@@ -198,8 +207,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sDz = smem + Cfg::kOffDz;
-    float* sLx = reinterpret_cast<float*>(smem + Cfg::kOffLx);
-    float* sG = reinterpret_cast<float*>(smem + Cfg::kOffG);
+    uint2* sX = reinterpret_cast<uint2*>(smem + Cfg::kOffX);
     float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
     uint64_t* full = bars;                uint64_t* empty = full + STAGES;
@@ -207,6 +215,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.trace && threadIdx.x == 0) a.trace[(384 + blockIdx.x / 32) * 64 + (blockIdx.x % 32) * 2] = gtime();
     // A unit is one CTA, or one 2-CTA cluster (PAIR; cr = this CTA's half of the unit's rows).  CL consecutive units
     // form a group that shares the rows and splits the classes.  The group is not a hardware cluster: clusters of 4
     // strand ~16 of the 148 SMs (GPC packing); it only needs co-residency, which the cooperative launch gives.
@@ -232,6 +241,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (HAS_BIAS) {
         for (int i = threadIdx.x; i < BN; i += Cfg::kThreads) sBias[i] = (i < ncols) ? a.bias[n0 + i] : 0.f;
     }
+    for (int i = threadIdx.x; i < 2 * BM * 8; i += Cfg::kThreads) sX[i] = make_uint2(0u, 0u);     // epoch 0 = nothing published
     if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
     tc_fence_before_sync();
     if (PAIR) cluster_sync_(); else __syncthreads();
@@ -249,6 +259,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * Cfg::kStageBytes;
                     if (elect_one()) {
+                        // The feature rows come from HBM and the pipeline is only STAGES deep: pull the NEXT tile's rows
+                        // into L2 while this tile is computed (each unit of the group takes every CL-th k-block).
+                        if ((kb % CL) == (int)rank && tile + n_clusters < n_tiles)
+                            tma_prefetch_l2_2d(&tm_x, kb * BK, (tile + n_clusters) * TM + cr * BM);
                         if (PAIR) {
                             // both CTAs' bytes are counted on the leader's barrier (the MMA issuer waits there)
                             if (cr == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
@@ -342,6 +356,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             for (int g = 0; g < G; ++g)
                 if (c_base + g * 32 < ncols) tmem_ld32(t_row + c_base + g * 32, v[g]);
             tmem_ld_wait();
+            if (tr && blockIdx.x == 0) a.trace[256 * 64 + 128 + it * 8 + 0] = gtime();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_leader(&t_empty[buf]); else mbar_arrive(&t_empty[buf]); }
@@ -378,6 +393,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     }
                 }
             }
+            if (tr && blockIdx.x == 0) a.trace[256 * 64 + 128 + it * 8 + 1] = gtime();
             // ---- e = exp(z - m_slice) in place; partial sums with 4-way ILP.  The label's logit comes out of a select
             //      tree and the sum of the logits (uniform-target rows) runs unconditionally: per-element predicates cost
             //      more instructions than the arithmetic they guard. ----
@@ -412,39 +428,41 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 4] = gtime();
             const float m_slice = m, zy_own = zy;
-            // ---- combine the column slices of this CTA (shared memory), then the units of the group (L2) ----
-            {
-                float* lx = sLx + (((it & 1) * EW + h) * BM + r_in_tile) * kStatFloats;
-                lx[0] = m; lx[1] = s; lx[2] = zy; lx[3] = sumz; lx[4] = mv; lx[5] = __int_as_float(am);
-                asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
-                m = -INFINITY; mv = -INFINITY; am = 0x7fffffff;
-                float pm[EW];
+            // ---- the two owners of a row (column halves h = 0, 1) meet through (value, epoch) words in shared memory, the
+            //      units of a group through the same kind of words in L2: pairwise waits only, no CTA-wide barrier (with
+            //      bar.sync every warp waited for the slowest warp AND for the L2 round trip of the polling threads) ----
+            const uint32_t eps = it + 1;                                   // shared-memory epoch (this launch only)
+            uint2* sx = sX + ((it & 1) * BM + r_in_tile) * 8;              // [0..5] h=1 -> h=0 statistics, [6..7] h=0 -> h=1 row max / sum
+            float m_cta = m;                                               // max over this unit's columns (arg-max fold at the end)
+            if (h == 1) {
+                sts_ll(sx + 0, m, eps); sts_ll(sx + 1, s, eps); sts_ll(sx + 2, zy, eps);
+                sts_ll(sx + 3, sumz, eps); sts_ll(sx + 4, mv, eps); sts_ll(sx + 5, __int_as_float(am), eps);
+                uint2 g0, g1;
+                do { g0 = lds_ll(sx + 6); g1 = lds_ll(sx + 7); if (g0.y != eps || g1.y != eps) __nanosleep(32); } while (g0.y != eps || g1.y != eps);
+                m = __uint_as_float(g0.x); s = __uint_as_float(g1.x);
+            } else {
+                {
+                    uint2 w[kStatFloats];
+                    bool ok;
+                    do {
+                        ok = true;
 #pragma unroll
-                for (int e = 0; e < EW; ++e) {
-                    const float* o = sLx + (((it & 1) * EW + e) * BM + r_in_tile) * kStatFloats;
-                    pm[e] = o[0];
-                    const int oam = __float_as_int(o[5]);
-                    if (pm[e] > m || (pm[e] == m && oam < am)) am = oam;
-                    m = fmaxf(m, pm[e]);
-                    mv = fmaxf(mv, o[4]);
+                        for (int j = 0; j < kStatFloats; ++j) { w[j] = lds_ll(sx + j); ok = ok && (w[j].y == eps); }
+                    } while (!ok);
+                    const float pm = __uint_as_float(w[0].x);
+                    if (pm > m) am = (int)w[5].x;                          // the partner owns the higher columns: ties stay here
+                    const float mc = fmaxf(m, pm);
+                    s = s * fast_exp2((m - mc) * kLog2e) + __uint_as_float(w[1].x) * fast_exp2((pm - mc) * kLog2e);
+                    m = mc; m_cta = mc;
+                    zy += __uint_as_float(w[2].x); sumz += __uint_as_float(w[3].x); mv = fmaxf(mv, __uint_as_float(w[4].x));
                 }
-                s = 0.f; zy = 0.f; sumz = 0.f;
-#pragma unroll
-                for (int e = 0; e < EW; ++e) {
-                    const float* o = sLx + (((it & 1) * EW + e) * BM + r_in_tile) * kStatFloats;
-                    s += o[1] * fast_exp2((pm[e] - m) * kLog2e);
-                    zy += o[2]; sumz += o[3];
-                }
-            }
-            const float m_cta = m;              // max over this unit's columns (for the arg-max fold at the end)
-            if (CL > 1) {
-                // Through L2, not DSMEM: with the tensor pipe busy on the next tile, remote shared-memory stores and
-                // arrives to a peer SM took ~8 us per tile (measured).  One thread per row publishes (value, epoch)
-                // words and polls the peers' words of the same row: one L2 round trip, no flag, no fence.  Everybody
-                // needs the row max and sum of the whole head now; the other four statistics only feed the per-row
-                // outputs, which unit 0 collects AFTER the grad-logits are out (registers are free again by then).
-                float* sg = sG + ((it & 1) * BM + r_in_tile) * 2;
-                if (h == 0) {
+                if (tr && blockIdx.x == 0) a.trace[256 * 64 + 128 + it * 8 + 2] = gtime();
+                if (CL > 1) {
+                    // Through L2, not DSMEM: with the tensor pipe busy on the next tile, remote shared-memory stores and
+                    // arrives to a peer SM took ~8 us per tile (measured).  One thread per row publishes (value, epoch)
+                    // words and polls the peers' words of the same row: one L2 round trip, no flag, no fence.  Everybody
+                    // needs the row max and sum of the whole head now; the other four statistics only feed the per-row
+                    // outputs, which unit 0 collects AFTER the grad-logits are out (registers are free again by then).
                     const uint32_t ep = ep_base + it + 1;
                     uint2* xs = a.xch_stats + ((size_t)(xid * 2 + (it & 1)) * CL) * BM * kStatFloats;
                     uint2* dst = xs + ((size_t)rank * BM + r_in_tile) * kStatFloats;
@@ -472,10 +490,8 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     for (int d = 1; d < CL; ++d)
                         s += __uint_as_float(pv[d - 1][1].x) * fast_exp2((__uint_as_float(pv[d - 1][0].x) - mg) * kLog2e);
                     m = mg;
-                    sg[0] = m; sg[1] = s;
                 }
-                asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
-                if (h != 0) { m = sg[0]; s = sg[1]; }
+                sts_ll(sx + 6, m, eps); sts_ll(sx + 7, s, eps);
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 5] = gtime();
             // ---- un-scaled grad-logits  dz = (S p - T) / den = coef * e - T/den  -> bf16 -> swizzled smem -> TMA store ----
@@ -520,6 +536,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     }
                 }
             }
+            if (tr && blockIdx.x == 0) a.trace[256 * 64 + 128 + it * 8 + 3] = gtime();
             // ---- per-row outputs (unit 0 of the group): loss, p[target], max p over the valid columns, max p, arg-max ----
             if (rank == 0 && h == 0) {
                 if (CL > 1) {
@@ -569,30 +586,40 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 6] = gtime();
         }
-        if (lane == 0) tma_store_wait<0>();
-        // ---- deterministic loss reduction: quadrants in order, CTAs in order ----
+        if (lane == 0) tma_store_wait_read<0>();          // the staging buffers have been read; the data lands before the grid ends
+        // ---- deterministic loss reduction: quadrants in order inside a CTA; the last CTA to finish sums the CTAs' partials,
+        //      lane l taking CTAs l, l + 32, ... in order and a fixed shuffle tree on top (one warp, ~1 us; a single thread
+        //      walking all partials kept the whole grid alive for another ~6 us) ----
         __shared__ double s_loss[4];
+        __shared__ unsigned s_last;
         double wl = warp_sum(loss_acc);
         if (lane == 0 && h == 0) s_loss[q] = wl;
         asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
-        if (warp == kEpiWarp0 && lane == 0) {
-            a.partials[blockIdx.x] = ((s_loss[0] + s_loss[1]) + s_loss[2]) + s_loss[3];
-            __threadfence();
-            const unsigned t = atomicAdd(a.ticket, 1u);
-            if (t == gridDim.x - 1) {
+        if (warp == kEpiWarp0) {
+            if (lane == 0) {
+                a.partials[blockIdx.x] = ((s_loss[0] + s_loss[1]) + s_loss[2]) + s_loss[3];
+                __threadfence();
+                s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+            }
+            __syncwarp();
+            if (s_last) {
                 __threadfence();
                 double tot = 0.0;
-                for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(&a.partials[b]);
-                a.loss_num[0] = tot;
-                a.loss[0] = (float)(tot / a.den[0]);
-                *a.ticket = 0u;
-                if (CL > 1) *a.xch_epoch = ep_base + (uint32_t)((n_tiles + n_clusters - 1) / n_clusters) + 1u;
+                for (unsigned b = lane; b < gridDim.x; b += 32) tot += __ldcg(&a.partials[b]);
+                tot = warp_sum(tot);
+                if (lane == 0) {
+                    a.loss_num[0] = tot;
+                    a.loss[0] = (float)(tot / a.den[0]);
+                    *a.ticket = 0u;
+                    if (CL > 1) *a.xch_epoch = ep_base + (uint32_t)((n_tiles + n_clusters - 1) / n_clusters) + 1u;
+                }
             }
         }
     }
     tc_fence_before_sync();
     if (PAIR) cluster_sync_(); else __syncthreads();
     if (warp == 1) { if (PAIR) tmem_dealloc2(tbase, Cfg::kTmemCols); else tmem_dealloc(tbase, Cfg::kTmemCols); }
+    if (a.trace && threadIdx.x == 0) a.trace[(384 + blockIdx.x / 32) * 64 + (blockIdx.x % 32) * 2 + 1] = gtime();
 }
 
 // =================================================================================================
@@ -715,7 +742,7 @@ head_dx_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
-        if (lane == 0) tma_store_wait<0>();
+        if (lane == 0) tma_store_wait_read<0>();      // staging buffers read; the stores land before the grid ends
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -860,9 +887,17 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                         float g[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[2 * b + h][i]);
+                        if (dbg & 16) {                  // developer probe: conversion only, no staging
+                            float acc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) acc += g[i];
+                            if (acc == 12345.f) trace[0] = 1;
+                            continue;
+                        }
 #pragma unroll
                         for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
                     }
+                    if (dbg & (8 | 16)) continue;            // developer probe: no TMA store
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -873,7 +908,7 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             }
             if (tr) trace[blockIdx.x * 64 + tc * 8 + 4] = gtime();
         }
-        if (lane == 0) tma_store_wait<0>();
+        if (lane == 0) tma_store_wait_read<0>();      // staging buffers read; the stores land before the grid ends
     }
     tc_fence_before_sync();
     cluster_sync_();
@@ -978,6 +1013,113 @@ head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     if (warp == 1) tmem_dealloc(tbase, 256);
 }
 
+// =================================================================================================
+// dW partials with CTA pairs (cta_group::2): one 2-CTA cluster per 256 classes x 256 features x batch slice, M = 256
+// MMAs.  CTA r stages classes [128 r, +128) of the dZ block and features [128 r, +128) of the X block (32 KB per
+// k-block instead of 48 KB): the single-CTA kernel needs 96 B/clk of operand reads plus 96 B/clk of TMA fill from a
+// shared memory that delivers 128 B/clk; the pair needs 64 + 64.
+// =================================================================================================
+constexpr int kDw2Stages = 6;
+constexpr int kDw2StageBytes = 4 * kBoxBytes;                   // 32 KB: dZ 2 boxes + X 2 boxes, 64 batch rows each
+constexpr int kDw2OffBars = kDw2Stages * kDw2StageBytes;
+constexpr int kDw2SmemBytes = kDw2OffBars + (2 * kDw2Stages + 1) * 8 + 16 + 1024;
+static_assert(kDw2SmemBytes <= 232448, "dw2 kernel shared memory");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
+                int B, int K, int C, int splits, float* __restrict__ partials) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2OffBars);
+    uint64_t* full = bars; uint64_t* empty = full + kDw2Stages; uint64_t* t_full = empty + kDw2Stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank_();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDw2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(t_full, 1);
+        fence_barrier_init();
+        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_x);
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 256);
+    tc_fence_before_sync();
+    cluster_sync_();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const int n_tiles = (K + kDwBN - 1) / kDwBN;
+    const int unit = blockIdx.x >> 1;
+    const int sp = unit % splits, tile = unit / splits;
+    const int mt = tile / n_tiles, nt = tile % n_tiles;
+    const int kb_total = (B + BK - 1) / BK;
+    const int kb0 = (int)((int64_t)kb_total * sp / splits), kb1 = (int)((int64_t)kb_total * (sp + 1) / splits);
+
+    // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
+    if (warp == 0) {
+        uint32_t it = 0;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * kDw2StageBytes;
+            if (elect_one()) {
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDw2StageBytes);     // both CTAs' bytes land on the leader's barrier
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(st + j * kBoxBytes, &tm_dz, &full[s], mt * 256 + rank * 128 + j * 64, kb * BK);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + rank * 128 + j * 64, kb * BK);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(256, kDwBN, true, true);
+            uint32_t it = 0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const uint32_t s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after_sync();
+                const uint32_t a_addr = smem_u32(smem + s * kDw2StageBytes);
+                const uint64_t adesc = make_desc_mnmajor(a_addr, kBoxBytes), bdesc = make_desc_mnmajor(a_addr + 2 * kBoxBytes, kBoxBytes);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma2_bf16(tbase, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
+                    umma2_commit_mc(&empty[s]);
+                    if (kb == kb1 - 1) umma2_commit_mc(t_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int cls = mt * 256 + rank * 128 + q * 32 + lane;
+        mbar_wait_warp(t_full, 0);
+        tc_fence_after_sync();
+        float* dst = partials + ((size_t)sp * C + (size_t)(cls < C ? cls : 0)) * K + (size_t)nt * kDwBN;
+        const uint32_t t_row = tmem_addr(tbase, q * 32, 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kDwBN; c0 += 64) {
+            uint32_t v[2][32];
+            tmem_ld32(t_row + c0, v[0]);
+            tmem_ld32(t_row + c0 + 32, v[1]);
+            tmem_ld_wait();
+            if (cls < C) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (nt * kDwBN + c0 + h * 32 + i < K) {
+                            float4 o = make_float4(__uint_as_float(v[h][i]), __uint_as_float(v[h][i + 1]),
+                                                   __uint_as_float(v[h][i + 2]), __uint_as_float(v[h][i + 3]));
+                            *reinterpret_cast<float4*>(dst + c0 + h * 32 + i) = o;
+                        }
+                    }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    cluster_sync_();
+    if (warp == 1) tmem_dealloc2(tbase, 256);
+}
+
 // dW = g * sum_s partials[s]  (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
 dw_reduce_kernel(const float4* __restrict__ partials, int splits, size_t n4, const float* __restrict__ gscale,
@@ -1013,11 +1155,18 @@ db_kernel(const __nv_bfloat16* __restrict__ dz, int64_t lddz, int B, int C, cons
 }
 
 // ---- host --------------------------------------------------------------------------------------
-static int dw_splits(int B, int K, int C) {
-    const int mt = (C + BM - 1) / BM, nt = (K + kDwBN - 1) / kDwBN;
+static int g_head_pairs = 1;          // 1: GEMMs run on CTA pairs (cta_group::2) where a pair kernel exists; 0: single-CTA kernels
+// the dW GEMM runs on CTA pairs (256 classes per pair) when the head is wider than one single-CTA tile
+static bool dw_pairs(int C) { return g_head_pairs != 0 && C > BM; }
+
+// split-K factor of the dW GEMM: output tiles x splits fill the SMs (pairs) once
+static int dw_splits(int B, int K, int C, int force_pair = -1) {
+    const bool pair = force_pair < 0 ? dw_pairs(C) : (force_pair != 0 && C > BM);
+    const int mt = pair ? (C + 255) / 256 : (C + BM - 1) / BM, nt = (K + kDwBN - 1) / kDwBN;
     const int kb_total = (B + BK - 1) / BK;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
+    if (pair) sms /= 2;
     int s = sms / (mt * nt);
     if (s < 1) s = 1;
     if (s > 16) s = 16;
@@ -1089,7 +1238,6 @@ static int fwd_box_rows(int C, bool pair) { return (C <= 128 ? 128 : 256) / (pai
 using namespace osb;
 using namespace osb::head;
 
-static int g_head_pairs = 1;          // 1: GEMMs run on CTA pairs (cta_group::2) where a pair kernel exists; 0: single-CTA kernels
 // developer hook (not part of the public header): A/B switch between the single-CTA and the CTA-pair kernels
 extern "C" void osb_debug_set_head_pairs(int on) { g_head_pairs = on; }
 static thread_local bool g_dw_partials_only = false;   // set by osb_head_backward_dw_partials around its call
@@ -1101,7 +1249,9 @@ extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<l
 
 extern "C" size_t osb_head_workspace_bytes(int64_t B, int K, int C) {
     if (B < 0 || K <= 0 || C <= 0) return 0;
-    const int s = dw_splits((int)B, K, C);
+    // room for either GEMM path (the developer switch may change after the caller sized its workspace)
+    const int s0 = dw_splits((int)B, K, C, 0), s1 = dw_splits((int)B, K, C, 1);
+    const int s = s0 > s1 ? s0 : s1;
     return kWsOffDw + align_up((size_t)s * C * K * sizeof(float), 256) + 256;
 }
 
@@ -1214,12 +1364,19 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         CUtensorMap tdz, tx;
         OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 64), "dz (MN-major)");
         OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
-        rc = set_smem(head_dw_kernel, kDwSmemBytes);
-        if (rc) return rc;
         const int splits = dw_splits((int)B, K, C);
-        const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
-        head_dw_kernel<<<units, kThreads, kDwSmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
+        if (dw_pairs(C)) {
+            rc = set_smem(head_dw2_kernel, kDw2SmemBytes);
+            if (rc) return rc;
+            const int units = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN) * splits;
+            head_dw2_kernel<<<units * 2, kThreads, kDw2SmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
+        } else {
+            rc = set_smem(head_dw_kernel, kDwSmemBytes);
+            if (rc) return rc;
+            const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
+            head_dw_kernel<<<units, kThreads, kDwSmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
+        }
         OSB_LAUNCH_CHECK();
         if (dw) {
             const size_t n4 = (size_t)C * K / 4;

@@ -67,6 +67,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// global -> L2 only (no shared-memory destination, no completion): warms L2 for a tile that will be loaded later
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(m), "r"(c0), "r"(c1) : "memory");
+}
 // shared -> global, 2-D tile (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -185,9 +189,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
 }
-// arrive on the LEADER CTA's barrier at this offset (from either CTA of the pair)
+// Arrive on the LEADER CTA's barrier at this offset (from either CTA of the pair).  RELAXED: the barrier only hands a TMEM
+// accumulator back to the MMA warp, and the tcgen05 loads that read it are ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync.  The default .release.cluster compiles to MEMBAR.ALL.GPU in front of the arrive,
+// which waits for every global store the warp has in flight: ~2 us per tile in the epilogue warps (measured).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M x N tile, operand majors.

@@ -215,7 +215,7 @@ class ShardedHeadPlan:
         ``plan.loss`` the full-batch loss on every rank; ``plan.dx`` is this shard's d loss / d features."""
         p = self.plan
         p.label_stats(y, self._den_hook)
-        p.forward(x, w, y, bias)
+        p.forward(x, w, y, bias, want_pred=False)       # training step: no per-row predictions (HeadPlan.step)
         if self.peer is not None:
             p.backward_dw_partials(x)
             done = self.peer.run()

@@ -118,12 +118,14 @@ class HeadPlan:
         L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, self.B, self.K, self.C,
                L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False):
-        """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches."""
+    def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False, want_pred=False):
+        """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches.  A training step
+        has no use for the per-row arg-max / max probability (the reference's train loop reads the loss only,
+        train.py:124-139), so they are off unless ``want_pred``; p_target and p_max are always written."""
         if check:
             self._check(x, w, y)
         self.label_stats(y, den_scale_hook)
-        self.forward(x, w, y, bias)
+        self.forward(x, w, y, bias, want_pred=want_pred)
         self.backward_dx(x, w, gscale)
         self.backward_dw(x, w, gscale)
 

@@ -87,6 +87,33 @@ def test_head_fwd_bwd_vs_oracle(B, K, C, variant):
     assert np.mean(got == pred) > 0.999
 
 
+@pytest.mark.parametrize("B,K,C", [(256, 2048, 116), (1024, 2048, 152), (257, 512, 513), (384, 256, 1000)])
+def test_head_single_cta_kernels_vs_oracle(B, K, C):
+    """The single-CTA (cta_group::1) GEMM kernels stay in the library as the A/B reference of the CTA-pair kernels
+    (developer switch osb_debug_set_head_pairs); they must match the oracle too."""
+    from openset_imagenet_b200 import _lib as L
+    L.load().osb_debug_set_head_pairs(0)
+    try:
+        head, loss, xt, ref, _ = _run(B, K, C, "entropic", bias=True, seed=B + C + 1)
+    finally:
+        L.load().osb_debug_set_head_pairs(1)
+    assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
+    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
+    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < DW_TOL
+    assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+
+
+def test_head_many_tiles_per_cta_pair():
+    """More row tiles than CTA groups (several rounds of the persistent loops, both TMEM buffers, statistics-exchange
+    epochs that keep growing across launches on one workspace): 6000 x 256 -> 1000, three launches, against the oracle."""
+    B, K, C = 6000, 256, 1000
+    for seed in (1, 2, 3):
+        head, loss, xt, ref, _ = _run(B, K, C, "entropic", bias=False, seed=seed)
+        assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
+        assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
+        assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+
+
 @pytest.mark.parametrize("B,K,C", [(256, 2048, 116), (200, 256, 300), (384, 256, 1000)])
 def test_head_softmax_variant_and_bias(B, K, C):
     head, loss, xt, ref, _ = _run(B, K, C, "softmax", bias=True, seed=3)

@@ -9,11 +9,15 @@ from oracle import oracle as O
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+FLUSH_READ = os.environ.get("OSB_FLUSH") == "read"      # evict by reading (no dirty lines left in L2) instead of writing
+
 def timeit(fn, iters=20, warm=3, flush_l2=True):
     for _ in range(warm): fn()
     ts = []
     for _ in range(iters):
-        if flush_l2: flush.fill_(1)
+        if flush_l2:
+            if FLUSH_READ: flush.view(torch.int32).sum()
+            else: flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
@@ -44,6 +48,7 @@ def head_case(B, K, C, variant="entropic"):
                       num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), None, lddz, ws.data_ptr(), ws.numel(), st)
     def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, None, None, ws.data_ptr(), ws.numel(), st)
     def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, None, K, dw.data_ptr(), None, ws.data_ptr(), ws.numel(), st)
+    def bdwp(): L.call("osb_head_backward_dw_partials", dz.data_ptr(), lddz, x.data_ptr(), K, B, K, C, ws.data_ptr(), ws.numel(), st)
     def step(): lab(); fwd(); bdx(); bdw()
     fl = 2.0 * B * K * C
     print(f"--- head B={B} K={K} C={C} {variant}: GEMM flops each {fl/1e9:.2f} GF")
@@ -55,7 +60,7 @@ def head_case(B, K, C, variant="entropic"):
     def fwd1():
         lib.osb_debug_set_head_pairs(0); fwd(); lib.osb_debug_set_head_pairs(1)
     for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd 1-CTA", fwd1, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dx 1-CTA", bdx1, fl),
-                        ("dw(K3+reduce)", bdw, fl), ("dw 1-CTA", bdw1, fl), ("step", step, 3 * fl)]:
+                        ("dw(K3+reduce)", bdw, fl), ("dw 1-CTA", bdw1, fl), ("dw GEMM only", bdwp, fl), ("step", step, 3 * fl)]:
         med, mn = timeit(fn)
         med2, mn2 = timeit(fn, flush_l2=False)
         print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | warm med {med2:9.1f} us" + (f" | {f/med/1e6:8.1f} TF/s cold, {f/med2/1e6:8.1f} warm" if f else ""))

@@ -19,8 +19,12 @@ plan.label_stats(y)
 for _ in range(3): plan.forward(x, w, y)
 torch.cuda.synchronize()
 lib.osb_debug_set_head_trace(trace.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 plan.forward(x, w, y, write_dz=len(sys.argv) <= 4)
+e1.record()
 torch.cuda.synchronize()
+print(f"event time of the traced launch: {e0.elapsed_time(e1) * 1e3:.1f} us")
 lib.osb_debug_set_head_trace(None)
 t = trace.cpu().numpy()
 names = ["mma_start", "first_A_full", "mma_issued", "epi_tfull", "sweepA_done", "xchg_done", "sweepB_done"]
@@ -43,3 +47,16 @@ kb = t[256:258].reshape(-1)
 kb = kb[kb > 0]
 if len(kb) > 1:
     print("cycles between k-block issues (CTA 0, tiles 0-3):", " ".join(str(int(v)) for v in np.diff(kb)))
+
+sub = t[258:259].reshape(-1)[:32].reshape(4, 8)
+for it in range(4):
+    b = t[0][it * 8 + 3]
+    if b:
+        names2 = ["tfull", "ld_done", "max_done", "expA(4)", "partner", "xchg(5)", "dz_done", "outputs(6)"]
+        vals = [b, sub[it][0], sub[it][1], t[0][it * 8 + 4], sub[it][2], t[0][it * 8 + 5], sub[it][3], t[0][it * 8 + 6]]
+        print(f"cta 0 epilogue tile#{it} (ns after t_full): " + "  ".join(f"{n}={int(v - b)}" for n, v in zip(names2, vals)))
+
+se = t[384:392].reshape(-1)[:512].reshape(256, 2)
+se = se[se[:, 0] > 0]
+if len(se):
+    print(f"CTA entry: first {int(se[:, 0].min() - gbase)} last {int(se[:, 0].max() - gbase)}; CTA exit: first {int(se[:, 1].min() - gbase)} last {int(se[:, 1].max() - gbase)} (ns relative to the first MMA start); span {int(se[:, 1].max() - se[:, 0].min())} ns over {len(se)} CTAs")
