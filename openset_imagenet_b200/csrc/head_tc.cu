@@ -14,6 +14,7 @@
 //
 // Reference arithmetic: model.py:23-26,37-38 (linear), losses.py:16-29 / train.py:343,347 (losses),
 // train.py:177 + metrics.py:33-40 + util.py:109-111 (the per-row statistics), autograd of those.
+#include <stdlib.h>
 #include "osb_common.cuh"
 #include "row_modes.cuh"
 #include "tc05.cuh"
@@ -586,26 +587,26 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 6] = gtime();
         }
-        if (lane == 0) tma_store_wait_read<0>();          // the staging buffers have been read; the data lands before the grid ends
-        // ---- deterministic loss reduction: quadrants in order inside a CTA; the last CTA to finish sums the CTAs' partials,
-        //      lane l taking CTAs l, l + 32, ... in order and a fixed shuffle tree on top (one warp, ~1 us; a single thread
-        //      walking all partials kept the whole grid alive for another ~6 us) ----
-        __shared__ double s_loss[4];
-        __shared__ unsigned s_last;
-        double wl = warp_sum(loss_acc);
-        if (lane == 0 && h == 0) s_loss[q] = wl;
-        asm volatile("bar.sync 1, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
-        if (warp == kEpiWarp0) {
+        // ---- deterministic loss reduction without a CTA barrier: only the warps that accumulated row losses (unit 0 of a
+        //      group, column half 0) take part.  Each writes its partial and takes a ticket; the LAST warp of the grid sums
+        //      all partials in index order (lane l takes l, l + 32, ...; fixed shuffle tree on top) ----
+        const bool trx = a.trace && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32;
+        if (trx) a.trace[256 * 64 + 192 + 0] = gtime();
+        if (rank == 0 && h == 0) {
+            const unsigned n_part = (unsigned)n_clusters * (PAIR ? 2u : 1u) * 4u;
+            const double wl = warp_sum(loss_acc);
+            unsigned last = 0;
             if (lane == 0) {
-                a.partials[blockIdx.x] = ((s_loss[0] + s_loss[1]) + s_loss[2]) + s_loss[3];
+                a.partials[xid * 4 + q] = wl;
                 __threadfence();
-                s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+                last = (atomicAdd(a.ticket, 1u) == n_part - 1) ? 1u : 0u;
             }
-            __syncwarp();
-            if (s_last) {
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (trx) a.trace[256 * 64 + 192 + 2] = gtime();
+            if (last) {
                 __threadfence();
                 double tot = 0.0;
-                for (unsigned b = lane; b < gridDim.x; b += 32) tot += __ldcg(&a.partials[b]);
+                for (unsigned b = lane; b < n_part; b += 32) tot += __ldcg(&a.partials[b]);
                 tot = warp_sum(tot);
                 if (lane == 0) {
                     a.loss_num[0] = tot;
@@ -615,9 +616,13 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 }
             }
         }
+        if (lane == 0) tma_store_wait_read<0>();          // the staging buffers have been read; the data lands before the grid ends
+        if (trx) a.trace[256 * 64 + 192 + 1] = gtime();
     }
+    if (a.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) a.trace[256 * 64 + 200 + warp] = gtime();
     tc_fence_before_sync();
     if (PAIR) cluster_sync_(); else __syncthreads();
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[256 * 64 + 192 + 3] = gtime();
     if (warp == 1) { if (PAIR) tmem_dealloc2(tbase, Cfg::kTmemCols); else tmem_dealloc(tbase, Cfg::kTmemCols); }
     if (a.trace && threadIdx.x == 0) a.trace[(384 + blockIdx.x / 32) * 64 + (blockIdx.x % 32) * 2 + 1] = gtime();
 }
@@ -887,17 +892,10 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                         float g[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[2 * b + h][i]);
-                        if (dbg & 16) {                  // developer probe: conversion only, no staging
-                            float acc = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) acc += g[i];
-                            if (acc == 12345.f) trace[0] = 1;
-                            continue;
-                        }
 #pragma unroll
                         for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
                     }
-                    if (dbg & (8 | 16)) continue;            // developer probe: no TMA store
+                    if (dbg & 8) continue;                   // developer probe: staging without the TMA store (5.3 vs 6.3 us per tile)
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -1201,7 +1199,10 @@ static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
     // group must be resident while its peers spin on its statistics flags
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (CL > 1) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
+    // (developer switch for Nsight Compute, which fails to replay a launch that is both cooperative and clustered: the
+    // grid never exceeds the SM count, so on an otherwise idle GPU all CTAs are resident without the attribute too)
+    static const bool no_coop = getenv("OSB_NO_COOP_LAUNCH") != nullptr;
+    if (CL > 1 && !(no_coop && PAIR)) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
     if (PAIR) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na;

@@ -60,3 +60,10 @@ se = t[384:392].reshape(-1)[:512].reshape(256, 2)
 se = se[se[:, 0] > 0]
 if len(se):
     print(f"CTA entry: first {int(se[:, 0].min() - gbase)} last {int(se[:, 0].max() - gbase)}; CTA exit: first {int(se[:, 1].min() - gbase)} last {int(se[:, 1].max() - gbase)} (ns relative to the first MMA start); span {int(se[:, 1].max() - se[:, 0].min())} ns over {len(se)} CTAs")
+
+ex = t[259].reshape(-1)
+b = t[0][3 * 8 + 6]
+if b:
+    print("cta 0 exit path (ns after its last tile's epilogue end):", " ".join(f"{n}={int(ex[i] - b)}" for i, n in enumerate(["loop_end", "tma_wait", "ticket", "cluster_sync"]) if ex[i]),
+          "| warps reach the final sync:", " ".join(str(int(ex[8 + w] - b)) for w in range(10) if ex[8 + w]),
+          "| CTA0 entry->exit:", int(t[384][1] - t[384][0]))
