@@ -226,7 +226,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
     k_dx = statistics.mean(e[2].elapsed_time(e[3]) for e in evs) * 1e3
 
     gemm_flops = 2.0 * B * K * C
-    kernels = {"head_fwd_kernel": k_fwd, "head_dw_kernel+dw_reduce_kernel": k_dw, "head_dx_kernel": k_dx}
+    kernels = {"head_fwd_kernel": k_fwd, "head_dw2_kernel+dw_reduce_kernel": k_dw, "head_dx2_kernel": k_dx}
     dom = max(kernels, key=kernels.get)
     step_us = ms_per_step * 1e3
     roof = {

@@ -222,6 +222,21 @@ int osb_ccr_at_fpr(const double* ccr, const double* fpr, const int64_t* n_unique
                    const double* queries_host, int nq, int64_t* out_idx, double* out_fpr,
                    double* out_ccr, void* stream);
 
+/* ---- score / feature-norm histograms (util.py:202-228 get_histogram) ------------------------- *
+ * osb_hist_metrics: the per-row values the reference histograms.  Pass `scores` [N, ld] fp32 (metric 'score':
+ * kn_metric[i] = scores[i, gt[i]] for gt[i] >= 0, unk_metric[i] = max scores[i, :valid_cols] for gt[i] == unk_label;
+ * valid_cols = C - 1 reproduces drop_bg) OR `features` [N, ldf] fp32 with K columns (metric 'norm': the row's L2 norm,
+ * accumulated in fp64 in a fixed order, for both groups); the other pointer is NULL.  Rows outside a group get NaN.
+ * counts[2] int64 = rows in each group; minmax[4] fp32 = kn min, kn max, unk min, unk max (np.histogram takes its bin
+ * range from them; untouched sentinels when a group is empty -- check counts).
+ * osb_histogram: counts[n_edges-1] int64 of `values` in the bins given by `edges` (device doubles, ascending), with
+ * np.histogram's rules: edges[j] <= x < edges[j+1], last bin closed on the right, NaN / out-of-range dropped.
+ */
+int osb_hist_metrics(const float* scores, int64_t ld, const float* features, int64_t ldf, int K,
+                     const int64_t* gt, int64_t N, int C, int valid_cols, int64_t unk_label,
+                     float* kn_metric, float* unk_metric, int64_t* counts, float* minmax, void* stream);
+int osb_histogram(const float* values, int64_t n, const double* edges, int n_edges, int64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

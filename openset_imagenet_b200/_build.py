@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libosb.so")
 STAMP = os.path.join(CSRC, ".libosb.stamp")
-SOURCES = ["lib.cu", "loss_rows.cu", "confidence.cu", "oscr.cu", "head_tc.cu", "dw_allreduce.cu"]
+SOURCES = ["lib.cu", "loss_rows.cu", "confidence.cu", "oscr.cu", "hist.cu", "head_tc.cu", "dw_allreduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared",

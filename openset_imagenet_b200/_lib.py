@@ -53,6 +53,8 @@ SIGNATURES = {
     "osb_oscr_ratios": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "osb_oscr": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "osb_ccr_at_fpr": (_i, [_p, _p, _p, _i64, _p, _i, _p, _p, _p, _p]),
+    "osb_hist_metrics": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _i, _i, _i64, _p, _p, _p, _p, _p]),
+    "osb_histogram": (_i, [_p, _i64, _p, _i, _p, _p]),
 }
 
 _lock = threading.Lock()

@@ -1025,7 +1025,7 @@ static_assert(kDw2SmemBytes <= 232448, "dw2 kernel shared memory");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
-                int B, int K, int C, int splits, float* __restrict__ partials) {
+                const __grid_constant__ CUtensorMap tm_part, int B, int K, int C, int splits, long long* trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2OffBars);
@@ -1033,11 +1033,12 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank_();
+    if (trace && threadIdx.x == 0) trace[blockIdx.x * 8 + 0] = gtime();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kDw2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(t_full, 1);
         fence_barrier_init();
-        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_x);
+        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_part);
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 256);
     tc_fence_before_sync();
@@ -1088,34 +1089,45 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         }
     } else {
         const int q = warp & 3;
-        const int cls = mt * 256 + rank * 128 + q * 32 + lane;
         mbar_wait_warp(t_full, 0);
         tc_fence_after_sync();
-        float* dst = partials + ((size_t)sp * C + (size_t)(cls < C ? cls : 0)) * K + (size_t)nt * kDwBN;
+        if (trace && threadIdx.x == kEpiWarp0 * 32) trace[blockIdx.x * 8 + 1] = gtime();
+        // Every MMA has completed, so the operand stages are free: the warp stages its 32 classes x 256 features (fp32) there
+        // as eight 128B-swizzled boxes and hands them to TMA stores, which write whole lines of the partial matrix and clip
+        // the classes >= C (direct stores put one 16-byte piece per class row and instruction: 5.2 us per CTA, measured).
+        uint8_t* my_stage = smem + q * (8 * kStageWarpBytes);
         const uint32_t t_row = tmem_addr(tbase, q * 32, 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kDwBN; c0 += 64) {
+        for (int g = 0; g < kDwBN / 32; g += 2) {
             uint32_t v[2][32];
-            tmem_ld32(t_row + c0, v[0]);
-            tmem_ld32(t_row + c0 + 32, v[1]);
+            tmem_ld32(t_row + g * 32, v[0]);
+            tmem_ld32(t_row + g * 32 + 32, v[1]);
             tmem_ld_wait();
-            if (cls < C) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h) {
+                uint8_t* sbuf = my_stage + (g + h) * kStageWarpBytes;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (nt * kDwBN + c0 + h * 32 + i < K) {
-                            float4 o = make_float4(__uint_as_float(v[h][i]), __uint_as_float(v[h][i + 1]),
-                                                   __uint_as_float(v[h][i + 2]), __uint_as_float(v[h][i + 3]));
-                            *reinterpret_cast<float4*>(dst + c0 + h * 32 + i) = o;
-                        }
-                    }
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                        make_uint4(v[h][4 * c], v[h][4 * c + 1], v[h][4 * c + 2], v[h][4 * c + 3]);
             }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < kDwBN / 32; ++g)
+                tma_store_3d(&tm_part, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, mt * 256 + rank * 128 + q * 32, sp);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+        }
+        __syncwarp();
     }
+    if (trace && threadIdx.x == kEpiWarp0 * 32) trace[blockIdx.x * 8 + 2] = gtime();
     tc_fence_before_sync();
     cluster_sync_();
     if (warp == 1) tmem_dealloc2(tbase, 256);
+    if (trace && threadIdx.x == 0) trace[blockIdx.x * 8 + 3] = gtime();
 }
 
 // dW = g * sum_s partials[s]  (fixed order => deterministic)
@@ -1371,7 +1383,9 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
             rc = set_smem(head_dw2_kernel, kDw2SmemBytes);
             if (rc) return rc;
             const int units = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN) * splits;
-            head_dw2_kernel<<<units * 2, kThreads, kDw2SmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
+            CUtensorMap tpart;
+            OSB_TMAP(make_tmap_f32_3d(&tpart, partials, (uint64_t)splits, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW partials (store)");
+            head_dw2_kernel<<<units * 2, kThreads, kDw2SmemBytes, st>>>(tdz, tx, tpart, (int)B, K, C, splits, g_trace);
         } else {
             rc = set_smem(head_dw_kernel, kDwSmemBytes);
             if (rc) return rc;

@@ -76,6 +76,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
@@ -283,6 +287,22 @@ static inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t ro
     if (r != CUDA_SUCCESS) return (int)r;
     e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.box_rows = box_rows; e.box_cols = box_cols; e.map = *out; e.valid = true;
     return 0;
+}
+
+// 3-D fp32 tensor [planes, rows, cols] (row pitch `ld` elements, plane pitch rows * ld); box = 32 columns (128 bytes) x
+// box_rows rows x 1 plane, SWIZZLE_128B: the split-K partial matrices of the dW GEMM, stored tile by tile.
+static inline int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld,
+                                   uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t dims[3] = {cols, rows, planes};
+    cuuint64_t strides[2] = {ld * 4, rows * ld * 4};
+    cuuint32_t box[3] = {32, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
 }  // namespace osb

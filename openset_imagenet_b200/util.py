@@ -173,3 +173,71 @@ def ccr_at_fpr(ccr, fpr, queries=(1e-3, 1e-2, 0.1, 1.0), device=None):
         err = round(100 * abs(fv - q) / q, 1)
         out.append((i, fv, None if err >= 10.0 else cv))
     return out
+
+
+def get_histogram(array, unk_label=-1, metric='score', bins=100, drop_bg=False, log_space=False,
+                  geomspace_limits=(1, 1e2), device=None):
+    """Histograms of scores or feature norms, the reference's ``util.get_histogram`` (util.py:202-228) with the
+    same signature and return value ``(kn_hist, kn_edges, unk_hist, unk_edges)`` (numpy int64 counts, numpy edges).
+
+    ``array`` is the reference's npz dict (keys ``scores``, ``gt``, ``features``; numpy arrays or tensors).  One
+    kernel produces the per-row values (known rows: the target's score, ``unk_label`` rows: the row maximum; or the
+    feature norm for both) together with the min / max np.histogram derives its bin range from; the edges are then
+    numpy's own (``np.histogram_bin_edges`` on [min, max], or ``np.geomspace``), and a second kernel counts with
+    np.histogram's rules, so for metric 'score' the counts are bit-exact.  For metric 'norm' the norm is accumulated
+    in fp64 (the reference's float32 pairwise sum is not reproducible), so a value within one float32 ulp of an edge
+    may land in the neighbouring bin.
+    """
+    if metric not in ('score', 'norm'):
+        raise ValueError("metric must be 'score' or 'norm'")
+    src = array['scores'] if metric == 'score' else array['features']
+    if isinstance(src, torch.Tensor) and src.is_cuda:
+        dev = src.device
+    else:
+        dev = torch.device(device) if device is not None else default_device()
+    gt = _to_device(array['gt'], dev)
+    gt = gt.to(torch.int64).contiguous()            # gt.astype(np.int64), util.py:213
+    v = _to_device(src, dev, torch.float32)
+    if v.dim() != 2 or v.shape[0] != gt.shape[0]:
+        raise ValueError("scores / features must be [N, C] with one row per label")
+    if v.stride(1) != 1:
+        v = v.contiguous()
+    N, C = v.shape
+    if metric == 'score':
+        valid = C - 1 if drop_bg else C             # score[:, :-1], util.py:210-211
+        if valid < 1:
+            raise ValueError("no score column left")
+        if N and int(gt.max()) >= valid:
+            raise IndexError(f"label {int(gt.max())} is out of bounds for {valid} score columns")
+    kn = torch.empty(N, dtype=torch.float32, device=dev)
+    unk = torch.empty(N, dtype=torch.float32, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    minmax = torch.empty(4, dtype=torch.float32, device=dev)
+    st = L.stream_ptr(dev)
+    if metric == 'score':
+        L.call("osb_hist_metrics", L.ptr(v), v.stride(0), None, 0, 0, L.ptr(gt), N, C, valid, int(unk_label),
+               L.ptr(kn), L.ptr(unk), L.ptr(counts), L.ptr(minmax), st)
+    else:
+        L.call("osb_hist_metrics", None, 0, L.ptr(v), v.stride(0), C, L.ptr(gt), N, 0, 0, int(unk_label),
+               L.ptr(kn), L.ptr(unk), L.ptr(counts), L.ptr(minmax), st)
+    cnt = counts.cpu().numpy()
+    # the kernel keeps min / max as order-preserving integers; decode them on the host
+    mm_bits = minmax.view(torch.int32).cpu().numpy().astype(np.uint32)
+    mm = np.where(mm_bits & np.uint32(0x80000000), mm_bits & np.uint32(0x7fffffff), ~mm_bits).astype(np.uint32).view(np.float32)
+
+    def one(values, n, lo, hi):
+        if log_space:
+            edges = np.geomspace(geomspace_limits[0], geomspace_limits[1], num=bins)     # util.py:223-225
+        else:
+            rng = np.array([lo, hi], dtype=np.float32) if n else np.empty(0, dtype=np.float32)
+            edges = np.histogram_bin_edges(rng, bins=bins)
+        if not np.all(np.diff(edges) >= 0):
+            raise ValueError('`bins` must increase monotonically, when an array')
+        e = torch.from_numpy(np.ascontiguousarray(edges, dtype=np.float64)).to(dev)
+        out = torch.empty(len(edges) - 1, dtype=torch.int64, device=dev)
+        L.call("osb_histogram", L.ptr(values), N, L.ptr(e), len(edges), L.ptr(out), st)
+        return out.cpu().numpy(), edges
+
+    kn_hist, kn_edges = one(kn, int(cnt[0]), mm[0], mm[1])
+    unk_hist, unk_edges = one(unk, int(cnt[1]), mm[2], mm[3])
+    return kn_hist, kn_edges, unk_hist, unk_edges

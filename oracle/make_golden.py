@@ -211,13 +211,43 @@ def golden_oscr():
     return out
 
 
+def golden_hist():
+    """util.get_histogram (util.py:202-228) run from the reference on seeded arrays."""
+    U = ref_loader.load("util")
+    out = {}
+    rng = np.random.default_rng(11)
+    gt, s = O.make_oscr_case(1500, 24, seed=4)
+    feats = (rng.standard_normal((1500, 16)) * rng.uniform(0.5, 6.0, size=(1500, 1))).astype(np.float32)
+    arr = {"scores": s, "gt": gt.astype(np.float32), "features": feats}       # gt stored float32 as in the npz (train.py:212)
+    out["gt"], out["scores"], out["features"] = arr["gt"], s, feats
+    for name, kw in HIST_CASES.items():
+        a = dict(arr)
+        if kw.get("drop_bg"):
+            a["gt"] = np.where(arr["gt"] >= 23, 0, arr["gt"]).astype(np.float32)     # labels must fit the 23 columns left
+        kh, ke, uh, ue = U.get_histogram(a, **kw)
+        out[f"{name}_kn_hist"], out[f"{name}_kn_edges"] = kh, ke
+        out[f"{name}_unk_hist"], out[f"{name}_unk_edges"] = uh, ue
+    np.savez_compressed(os.path.join(OUT, "hist.npz"), **out)
+    return out
+
+
+HIST_CASES = {
+    "score_m1": dict(unk_label=-1, metric="score", bins=100),
+    "score_m2_b37": dict(unk_label=-2, metric="score", bins=37),
+    "score_dropbg": dict(unk_label=-1, metric="score", bins=50, drop_bg=True),
+    "score_log": dict(unk_label=-1, metric="score", bins=30, log_space=True, geomspace_limits=(1e-4, 1.0)),
+    "norm_m1": dict(unk_label=-1, metric="norm", bins=100),
+    "norm_log": dict(unk_label=-2, metric="norm", bins=100, log_space=True, geomspace_limits=(1, 1e2)),
+}
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not available; golden vectors can only be regenerated in the build container")
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    a, b, c = golden_losses(), golden_confidence(), golden_oscr()
-    print("wrote", len(a), len(b), len(c), "arrays to", OUT)
+    a, b, c, d = golden_losses(), golden_confidence(), golden_oscr(), golden_hist()
+    print("wrote", len(a), len(b), len(c), len(d), "arrays to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

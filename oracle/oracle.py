@@ -321,6 +321,30 @@ def ccr_at_fpr(ccr, fpr, queries=(1e-3, 1e-2, 0.1, 1.0)):
 # --------------------------------------------------------------------------------------
 # synthetic workloads of the BASELINE.json shapes (shared by tests and bench; numpy only)
 # --------------------------------------------------------------------------------------
+def get_histogram(array, unk_label=-1, metric='score', bins=100, drop_bg=False, log_space=False,
+                  geomspace_limits=(1, 1e2)):
+    """util.py:202-228: histograms of the known rows' target score and the unk_label rows' maximum score (metric
+    'score'), or of the feature norms of both groups (metric 'norm').  Returns (kn_hist, kn_edges, unk_hist, unk_edges)."""
+    score = np.asarray(array['scores'])
+    if drop_bg:                                            # util.py:210-211
+        score = score[:, :-1]
+    gt = np.asarray(array['gt']).astype(np.int64)          # util.py:212
+    norms = np.linalg.norm(np.asarray(array['features']), axis=1)      # util.py:213-214
+    kn = gt >= 0
+    unk = gt == unk_label
+    if metric == 'score':                                  # util.py:217-219
+        kn_metric = score[kn, gt[kn]]
+        unk_metric = np.amax(score[unk], axis=1)
+    elif metric == 'norm':                                 # util.py:220-222
+        kn_metric = norms[kn]
+        unk_metric = norms[unk]
+    if log_space:                                          # util.py:223-225
+        bins = np.geomspace(geomspace_limits[0], geomspace_limits[1], num=bins)
+    kn_hist, kn_edges = np.histogram(kn_metric, bins=bins)
+    unk_hist, unk_edges = np.histogram(unk_metric, bins=bins)
+    return kn_hist, kn_edges, unk_hist, unk_edges
+
+
 def make_labels(B: int, C: int, neg_frac: float = 1.0 / 3.0, seed: int = 0, neg_label: int = -1):
     rng = np.random.default_rng(seed)
     y = rng.integers(0, C, size=B, dtype=np.int64)

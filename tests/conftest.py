@@ -34,4 +34,4 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, f"{name}.npz")) for name in ("losses", "confidence", "oscr")}
+    return {name: np.load(os.path.join(GOLDEN, f"{name}.npz")) for name in ("losses", "confidence", "oscr", "hist")}

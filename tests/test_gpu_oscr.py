@@ -277,3 +277,55 @@ def test_oscr_plan_with_and_without_count_outputs():
     for r in (full, lean):
         np.testing.assert_array_equal(r.ccr[:n].cpu().numpy(), o_ccr)
         np.testing.assert_array_equal(r.fpr[:n].cpu().numpy(), o_fpr)
+
+
+# ---- util.get_histogram (util.py:202-228) ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["score_m1", "score_m2_b37", "score_dropbg", "score_log"])
+def test_get_histogram_scores_bit_exact_vs_reference_golden(golden, name):
+    from oracle.make_golden import HIST_CASES
+    from openset_imagenet_b200.util import get_histogram
+    g = golden["hist"]
+    kw = HIST_CASES[name]
+    gt = g["gt"]
+    if kw.get("drop_bg"):
+        gt = np.where(gt >= 23, 0, gt).astype(np.float32)
+    kh, ke, uh, ue = get_histogram({"scores": g["scores"], "gt": gt, "features": g["features"]}, **kw)
+    np.testing.assert_array_equal(kh, g[f"{name}_kn_hist"])
+    np.testing.assert_array_equal(uh, g[f"{name}_unk_hist"])
+    np.testing.assert_array_equal(ke, g[f"{name}_kn_edges"])
+    np.testing.assert_array_equal(ue, g[f"{name}_unk_edges"])
+    assert kh.dtype == np.int64 and uh.dtype == np.int64
+
+
+@pytest.mark.parametrize("name", ["norm_m1", "norm_log"])
+def test_get_histogram_norms_vs_reference_golden(golden, name):
+    """Feature norms are accumulated in fp64 on the GPU (the reference's float32 pairwise sum is not reproducible), so a
+    norm within one float32 ulp of an edge may change bins: totals are exact, at most a few counts move to a neighbour."""
+    from oracle.make_golden import HIST_CASES
+    from openset_imagenet_b200.util import get_histogram
+    g = golden["hist"]
+    kw = HIST_CASES[name]
+    kh, ke, uh, ue = get_histogram({"scores": g["scores"], "gt": g["gt"], "features": g["features"]}, **kw)
+    for got, ref in ((kh, g[f"{name}_kn_hist"]), (uh, g[f"{name}_unk_hist"])):
+        assert abs(int(got.sum()) - int(ref.sum())) <= 2
+        assert np.abs(np.cumsum(got) - np.cumsum(ref)).max() <= 2
+    np.testing.assert_allclose(ke, g[f"{name}_kn_edges"], rtol=1e-6)
+    np.testing.assert_allclose(ue, g[f"{name}_unk_edges"], rtol=1e-6)
+
+
+def test_get_histogram_large_and_empty_groups():
+    """1M x 116 scores against the oracle (numpy), and a set without unknowns (np.histogram's (0, 1) default range)."""
+    from openset_imagenet_b200.util import get_histogram
+    gt, s = O.make_oscr_case(1_000_000, 116, seed=0)
+    arr = {"scores": s, "gt": gt, "features": np.zeros((len(gt), 1), dtype=np.float32)}
+    for unk in (-1, -2):
+        got = get_histogram(arr, unk_label=unk, bins=100)
+        ref = O.get_histogram(arr, unk_label=unk, bins=100)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a, b)
+    small = {"scores": s[:100], "gt": np.abs(gt[:100]), "features": np.zeros((100, 1), dtype=np.float32)}
+    got = get_histogram(small, bins=10)
+    ref = O.get_histogram(small, bins=10)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+    assert got[2].sum() == 0

@@ -150,6 +150,23 @@ def test_ccr_at_fpr(golden, name):
         assert (c is None and np.isnan(row[3])) or c == row[3]
 
 
+@pytest.mark.parametrize("name", ["score_m1", "score_m2_b37", "score_dropbg", "score_log", "norm_m1", "norm_log"])
+def test_get_histogram(golden, name):
+    """oracle.get_histogram against the reference's util.get_histogram (util.py:202-228) on the committed vectors."""
+    from oracle.make_golden import HIST_CASES
+    g = golden["hist"]
+    kw = HIST_CASES[name]
+    gt = g["gt"]
+    if kw.get("drop_bg"):
+        gt = np.where(gt >= 23, 0, gt).astype(np.float32)
+    kh, ke, uh, ue = O.get_histogram({"scores": g["scores"], "gt": gt, "features": g["features"]}, **kw)
+    np.testing.assert_array_equal(kh, g[f"{name}_kn_hist"])
+    np.testing.assert_array_equal(uh, g[f"{name}_unk_hist"])
+    np.testing.assert_array_equal(ke, g[f"{name}_kn_edges"])
+    np.testing.assert_array_equal(ue, g[f"{name}_unk_edges"])
+    assert kh.sum() > 0 and uh.sum() > 0
+
+
 def test_bf16_round():
     import torch
     a = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 37
