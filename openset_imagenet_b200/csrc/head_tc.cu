@@ -253,6 +253,12 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // ------------------------------ TMA producer ------------------------------
         // (issue loops run warp-converged with one elected lane issuing, see the MMA issuer below)
         if (ncols > 0) {
+            // the first tile has nobody to prefetch it: ask for all of its feature rows at once (the units of the group
+            // share the k-blocks), so that HBM latency is paid once and not once per pipeline refill
+            if (cluster_id < n_tiles && elect_one()) {
+                for (int kb = (int)rank; kb < n_kb; kb += CL) tma_prefetch_l2_2d(&tm_x, kb * BK, cluster_id * TM + cr * BM);
+            }
+            __syncwarp();
             uint32_t it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
