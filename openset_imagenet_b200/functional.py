@@ -97,19 +97,38 @@ class HeadPlan:
                L.ptr(gscale), None, self.K, L.ptr(self.dw), L.ptr(self.db), L.ptr(self.ws), self.ws.numel(),
                L.stream_ptr(self.dev))
 
-    def capture(self, x, w, y, bias=None, gscale=None):
+    def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None):
         """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five
         kernels on the CURRENT CONTENTS of those tensors with a single launch call.  The small-batch configurations
         (B <= 1024) are bound by launch latency, not by the kernels, so this is the path to use in a training loop."""
         self._check(x, w, y)
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
+        # Small batches leave most SMs idle and every kernel is a few microseconds of latency: dX and dW only depend on
+        # dZ, so they become parallel branches of the graph.  Large batches fill the GPU with either kernel and stay serial.
+        fork = self.B <= 4096 if parallel_backward is None else bool(parallel_backward)
+        branch = torch.cuda.Stream(device=self.dev) if fork else None
+
+        def body():
+            if not fork:
+                self.step(x, w, y, bias, gscale)
+                return
+            self.label_stats(y)
+            self.forward(x, w, y, bias, want_pred=False)
+            branch.wait_stream(side)
+            with torch.cuda.stream(branch):
+                self.backward_dw(x, w, gscale)
+            self.backward_dx(x, w, gscale)
+            side.wait_stream(branch)
+
         with torch.cuda.stream(side):
-            self.step(x, w, y, bias, gscale)                 # warm-up outside capture (function attributes, descriptors)
+            body()                                           # warm-up outside capture (function attributes, descriptors)
             side.synchronize()
+            if branch is not None:
+                branch.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                self.step(x, w, y, bias, gscale)
+                body()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         return graph
 
