@@ -901,7 +901,9 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 #pragma unroll
                         for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
                     }
-                    if (dbg & 8) continue;                   // developer probe: staging without the TMA store (5.3 vs 6.3 us per tile)
+                    // (developer probe: staging without the store gives 5.3 instead of 6.3 us per tile; coalesced LSU stores of the
+                    //  staged box instead of TMA give the same 6.3 -- it is the output traffic itself, not the TMA unit)
+                    if (dbg & 8) continue;
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {

@@ -53,6 +53,7 @@ def head_case(B, K, C, variant="entropic"):
     fl = 2.0 * B * K * C
     print(f"--- head B={B} K={K} C={C} {variant}: GEMM flops each {fl/1e9:.2f} GF")
     lib = L.load()
+    lib.osb_debug_set_head_dbg(int(os.environ.get('OSB_DBG', '0')))
     def bdx1():
         lib.osb_debug_set_head_pairs(0); bdx(); lib.osb_debug_set_head_pairs(1)
     def bdw1():
