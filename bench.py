@@ -226,7 +226,10 @@ def run_head(args, cfg, rank, world, dev, peaks):
     k_dx = statistics.mean(e[2].elapsed_time(e[3]) for e in evs) * 1e3
 
     gemm_flops = 2.0 * B * K * C
-    kernels = {"head_fwd_kernel": k_fwd, "head_dw2_kernel+dw_reduce_kernel": k_dw, "head_dx2_kernel": k_dx}
+    # batches of up to ~15 row tiles of a head of <= 256 classes take the split-K forward (cluster of 8 CTAs per tile)
+    splitk = C <= 256 and K >= 512 and (B + 127) // 128 <= sp._L.load().osb_debug_head_splitk_max_clusters()
+    kernels = {"head_fwd_splitk_kernel" if splitk else "head_fwd_kernel": k_fwd,
+               "head_dw2_kernel+dw_reduce_kernel": k_dw, "head_dx2_kernel": k_dx}
     dom = max(kernels, key=kernels.get)
     step_us = ms_per_step * 1e3
     roof = {

@@ -1172,6 +1172,276 @@ db_kernel(const __nv_bfloat16* __restrict__ dz, int64_t lddz, int B, int C, cons
     }
 }
 
+// =================================================================================================
+// forward for small batches: split-K over a cluster of 8 CTAs, reduce-scatter through distributed shared memory
+// =================================================================================================
+// With B <= 2048 rows the persistent kernel above keeps at most 8 CTA pairs busy, and each of them walks all of K
+// (one 256-row tile: ~22 us for K = 2048, whatever the tensor pipe could do).  Here a cluster of 8 CTAs owns one
+// 128-row tile: CTA r multiplies k-blocks [n_kb r / 8, n_kb (r + 1) / 8) into a 128 x C partial in its TMEM, the
+// partials are reduce-scattered through distributed shared memory (CTA r ends up with rows [16 r, +16) of the tile, the 8
+// partials of a row summed in rank order: deterministic), and 8 threads per row run the same softmax / loss /
+// grad-logits epilogue as head_fwd_kernel.  Every operand byte is loaded by exactly one CTA of the cluster.
+constexpr int kSkS = 8;                                          // CTAs per cluster = K slices = row owners
+constexpr int kSkRows = BM / kSkS;                               // rows of the tile a CTA owns after the reduce-scatter
+constexpr int kSkLanes = 128 / kSkRows;                          // epilogue threads per owned row
+constexpr int kSkStages = 4;
+constexpr int kSkBN = 256;                                       // widest head of this path = TMEM columns
+constexpr int kSkStageBytes = kABytes + kSkBN * BK * 2;          // 48 KB: X 128 rows + W up to 256 rows, 128 B each
+constexpr int kSkOffBars = kSkStages * kSkStageBytes;            // the stages double as the exchange buffer (128 KB at most)
+constexpr int kSkOffLoss = kSkOffBars + (2 * kSkStages + 1) * 8 + 16;
+constexpr int kSkSmemBytes = kSkOffLoss + kSkRows * 8 + 1024;
+static_assert(kSkS * (kSkBN / 4) * kSkRows * 16 <= kSkStages * kSkStageBytes, "exchange buffer must fit the operand stages");
+static_assert(kSkSmemBytes <= 232448, "split-K forward shared memory");
+static_assert(kSkLanes == 8, "the row epilogue reduces over 8 lanes");
+
+__device__ __forceinline__ void st_peer_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+template <int W> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+template <int W> __device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+template <bool HAS_BIAS>
+__global__ void __cluster_dims__(kSkS, 1, 1) __launch_bounds__(kThreads, 1)
+head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const FwdArgs a,
+                       __nv_bfloat16* __restrict__ dz, int64_t lddz) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSkOffBars);
+    uint64_t* full = bars; uint64_t* empty = full + kSkStages; uint64_t* t_full = empty + kSkStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+    double* sLoss = reinterpret_cast<double*>(smem + kSkOffLoss);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank_();
+    const int tile = (int)(blockIdx.x / kSkS);
+    const int n_kb = (a.K + BK - 1) / BK;
+    const int kb0 = n_kb * rank / kSkS, kb1 = n_kb * (rank + 1) / kSkS;
+    const bool has_k = kb1 > kb0;
+    const int ncolsN = (a.C + 15) & ~15;            // UMMA N = rows of the W box
+    const int ncolsP = (a.C + 31) & ~31;            // columns drained and exchanged (whole 32-column TMEM loads)
+    const int nc4 = ncolsP >> 2;                    // float4 groups per row; a multiple of 8
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSkStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(t_full, 1);
+        fence_barrier_init();
+        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kSkBN);
+    tc_fence_before_sync();
+    cluster_sync_();
+    tc_fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer: this CTA's k-blocks of the X tile and of W ----------------------
+        const uint32_t stage_tx = (uint32_t)(kABytes + ncolsN * BK * 2);
+        uint32_t it = 0;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t s = it % kSkStages, ph = (it / kSkStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * kSkStageBytes;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&full[s], stage_tx);
+                tma_load_2d(st, &tm_x, &full[s], kb * BK, tile * BM);
+                tma_load_2d(st + kABytes, &tm_w, &full[s], kb * BK, 0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer (warp-converged loop, one elected lane issues) ----------------------
+        const uint32_t idesc = make_idesc_bf16(BM, ncolsN, false, false);
+        uint32_t it = 0;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t s = it % kSkStages, ph = (it / kSkStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32(smem + s * kSkStageBytes);
+            const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_kmajor(a_addr + kABytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tbase, adesc + 2 * k, bdesc + 2 * k, idesc, (it | (uint32_t)k) != 0u);
+                umma_commit(&empty[s]);
+                if (kb == kb1 - 1) umma_commit(t_full);
+            }
+            __syncwarp();
+        }
+    } else if (has_k) {
+        mbar_wait_warp(t_full, 0);
+        tc_fence_after_sync();
+    }
+    // every MMA of every CTA of the cluster has completed (the epilogue warps arrive after their t_full): the operand
+    // stages of all 8 CTAs are free and become the exchange buffer  [source rank][float4 group][owned row] x 16 bytes
+    cluster_sync_();
+
+    if (warp >= kEpiWarp0) {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                                  // row of the partial tile = TMEM lane
+        const uint32_t peer = map_to_peer(smem_u32(smem), (uint32_t)(r / kSkRows));
+        const uint32_t dst0 = peer + (uint32_t)(((rank * nc4) * kSkRows + (r % kSkRows)) * 16);
+        const uint32_t t_row = tmem_addr(tbase, q * 32, 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncolsP; c0 += 32) {
+            uint32_t v[32];
+            if (has_k) {
+                tmem_ld32(t_row + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                st_peer_v4(dst0 + (uint32_t)((((c0 >> 2) + i) * kSkRows) * 16), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    }
+    tc_fence_before_sync();
+    cluster_sync_();                                                  // partials delivered (release / acquire at cluster scope)
+
+    if (warp >= kEpiWarp0) {
+        const int te = threadIdx.x - kEpiWarp0 * 32;
+        const int row16 = te / kSkLanes, sub = te % kSkLanes;
+        const int row = tile * BM + rank * kSkRows + row16;
+        const bool row_ok = row < a.B;
+        const int64_t y = row_ok ? a.y[row] : -1;
+        const float s_uniform = a.t_uniform * (float)a.C;
+        RowMode rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, s_uniform);
+        if (!row_ok) { rm.mode = kRowIgnored; rm.omega = 0.f; }
+        const float inv_den = (float)(1.0 / a.den[0]);
+        const float4* rbuf = reinterpret_cast<const float4*>(smem);
+        constexpr int NJ = kSkBN / 32;                                // float4 groups per thread, at most
+        const int nj = nc4 / kSkLanes;
+        // thread (row, sub) owns the float4 groups sub, sub + 8, ...: logits = the 8 partials summed in rank order
+        float z[NJ][4];
+        float m = -INFINITY, mv = -INFINITY;
+        int am = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (j < nj) {
+                const int c4 = sub + kSkLanes * j;
+                float4 acc = rbuf[(size_t)(c4 * kSkRows + row16)];
+#pragma unroll
+                for (int src = 1; src < kSkS; ++src) {
+                    const float4 p = rbuf[(size_t)((src * nc4 + c4) * kSkRows + row16)];
+                    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+                }
+                z[j][0] = acc.x; z[j][1] = acc.y; z[j][2] = acc.z; z[j][3] = acc.w;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = 4 * c4 + e;
+                    float v = z[j][e];
+                    if (HAS_BIAS) v += (col < a.C) ? a.bias[col] : 0.f;
+                    if (col >= a.C) v = -INFINITY;
+                    z[j][e] = v;
+                    if (v > m) { m = v; am = col; }               // columns ascend inside a thread: first arg-max
+                    if (col < a.valid_cols) mv = fmaxf(mv, v);
+                }
+            }
+        }
+        group_argmax<kSkLanes>(m, am);                                // ties go to the smaller column (numpy)
+        mv = group_max<kSkLanes>(mv);
+        float s = 0.f, sumz = 0.f, zy = 0.f;
+        const float mb = m * kLog2e;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (j < nj) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = 4 * (sub + kSkLanes * j) + e;
+                    const float v = z[j][e];
+                    if (col < a.C) sumz += v;
+                    if ((int64_t)col == y) zy = v;
+                    const float ex = fast_exp2(fmaf(v, kLog2e, -mb));     // masked columns: exp2(-inf) = 0
+                    s += ex;
+                    z[j][e] = ex;
+                }
+            }
+        }
+        s = group_sum<kSkLanes>(s); sumz = group_sum<kSkLanes>(sumz); zy = group_sum<kSkLanes>(zy);
+        // ---- un-scaled grad-logits  dz = (S p - T) / den = coef * e - T / den  (bf16, 8-byte stores: 4 columns) ----
+        if (a.write_dz && row_ok) {
+            const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
+            const float coef = live ? inv_den * rm.omega / s : 0.f;
+            const float t_all = (rm.mode == kRowUniform) ? inv_den * a.t_uniform : 0.f;
+            const float t_hot = (rm.mode == kRowOneHot) ? inv_den * rm.omega : 0.f;
+            __nv_bfloat16* drow = dz + (int64_t)row * lddz;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (j < nj) {
+                    const int col0 = 4 * (sub + kSkLanes * j);
+                    if (col0 < a.C) {
+                        float g[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            g[e] = fmaf(coef, z[j][e], -t_all) - (((int64_t)(col0 + e) == y) ? t_hot : 0.f);
+                        if (col0 + 4 <= a.C) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
+                            uint2 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                            *reinterpret_cast<uint2*>(drow + col0) = u;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (col0 + e < a.C) drow[col0 + e] = __float2bfloat16_rn(g[e]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- per-row outputs and the row's loss term ----
+        if (sub == 0) {
+            double rl = 0.0;
+            if (row_ok) {
+                const float lse = m + fast_log2(s) * kLn2;
+                const bool is_col = (y >= 0 && y < a.C);
+                float rowloss = 0.f;
+                if (rm.mode == kRowOneHot) rowloss = rm.omega * (lse - zy);
+                else if (rm.mode == kRowUniform) rowloss = a.t_uniform * ((float)a.C * lse - sumz);
+                else if (rm.mode == kRowBad) rowloss = __int_as_float(0x7fc00000);
+                rl = (double)rowloss;
+                if (a.row_ptgt) a.row_ptgt[row] = is_col ? fast_exp2((zy - lse) * kLog2e) : 0.f;
+                if (a.row_pmax) a.row_pmax[row] = fast_exp2((mv - lse) * kLog2e);
+                if (a.row_pmax_all) a.row_pmax_all[row] = fast_exp2((m - lse) * kLog2e);
+                if (a.row_pred) a.row_pred[row] = am;
+            }
+            sLoss[row16] = rl;
+        }
+        epi_bar_sync();
+        // ---- deterministic loss: rows in order inside the CTA, CTAs in index order by the last one out ----
+        if (warp == kEpiWarp0) {
+            unsigned last = 0;
+            if (lane == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int i = 0; i < kSkRows; ++i) t += sLoss[i];
+                a.partials[blockIdx.x] = t;
+                __threadfence();
+                last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+            }
+            last = __shfl_sync(kFull, last, 0);
+            if (last) {
+                __threadfence();
+                double tot = 0.0;
+                for (unsigned b = lane; b < gridDim.x; b += 32) tot += __ldcg(&a.partials[b]);
+                tot = warp_sum(tot);
+                if (lane == 0) {
+                    a.loss_num[0] = tot;
+                    a.loss[0] = (float)(tot / a.den[0]);
+                    *a.ticket = 0u;
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, kSkBN);
+}
+
 // ---- host --------------------------------------------------------------------------------------
 static int g_head_pairs = 1;          // 1: GEMMs run on CTA pairs (cta_group::2) where a pair kernel exists; 0: single-CTA kernels
 // the dW GEMM runs on CTA pairs (256 classes per pair) when the head is wider than one single-CTA tile
@@ -1261,6 +1531,37 @@ using namespace osb::head;
 
 // developer hook (not part of the public header): A/B switch between the single-CTA and the CTA-pair kernels
 extern "C" void osb_debug_set_head_pairs(int on) { g_head_pairs = on; }
+// developer hook: 0 sends small batches through the persistent kernels too (A/B reference of the split-K forward)
+static int g_head_splitk = 1;
+extern "C" void osb_debug_set_head_splitk(int on) { g_head_splitk = on; }
+// the split-K forward takes batches whose 128-row tiles x 8 CTAs fit the GPU at once (B <= 2048), heads of one tile
+// (C <= 256) and at least one k-block per CTA of the cluster
+// clusters of 8 CTAs (one CTA per SM: ~193 KB of shared memory) that the device keeps resident at once; measured on
+// B200: a second wave of clusters costs more than the persistent kernel, so larger batches stay there
+static int splitk_max_clusters() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    int n = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kSkS * 32); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSkSmemBytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = kSkS; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    if (cudaFuncSetAttribute(head_fwd_splitk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, head_fwd_splitk_kernel<false>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cached = n;
+    return cached;
+}
+extern "C" int osb_debug_head_splitk_max_clusters(void) { return splitk_max_clusters(); }
+static bool fwd_use_splitk(int64_t B, int K, int C) {
+    if (!g_head_splitk || C > kSkBN || K < BK * kSkS) return false;
+    const int64_t tiles = (B + BM - 1) / BM;
+    return tiles * kSkS <= cta_limit() && tiles <= splitk_max_clusters();
+}
 static thread_local bool g_dw_partials_only = false;   // set by osb_head_backward_dw_partials around its call
 static long long* g_trace = nullptr;
 static int g_dbg = 0;
@@ -1314,9 +1615,10 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     CUtensorMap tx, tw;
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, BM), "x");
     const bool pair = g_head_pairs != 0;
-    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, fwd_box_rows(C, pair)), "w");
+    const bool splitk = fwd_use_splitk(B, K, C);
+    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, splitk ? (uint32_t)((C + 15) & ~15) : (uint32_t)fwd_box_rows(C, pair)), "w");
     CUtensorMap tdz = tx;       // placeholder when no grad-logits are written
-    if (dz) OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 32), "dz (store)");
+    if (dz && !splitk) OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 32), "dz (store)");
     FwdArgs a;
     a.bias = bias; a.y = y; a.class_w = class_w; a.B = (int)B; a.K = K; a.C = C; a.variant = variant;
     a.t_uniform = (float)(unk_weight / (double)C);
@@ -1329,6 +1631,18 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.xch_epoch = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffEpoch);
     a.xch_stats = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + kWsOffStats);
     a.trace = g_trace;
+    if (splitk) {
+        const int grid = (int)((B + BM - 1) / BM) * kSkS;
+        if (bias) {
+            rc = set_smem(head_fwd_splitk_kernel<true>, kSkSmemBytes); if (rc) return rc;
+            head_fwd_splitk_kernel<true><<<grid, kThreads, kSkSmemBytes, st>>>(tx, tw, a, reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+        } else {
+            rc = set_smem(head_fwd_splitk_kernel<false>, kSkSmemBytes); if (rc) return rc;
+            head_fwd_splitk_kernel<false><<<grid, kThreads, kSkSmemBytes, st>>>(tx, tw, a, reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+        }
+        OSB_LAUNCH_CHECK();
+        return OSB_OK;
+    }
     if (pair) {
         if (C <= 128) return launch_fwd<128, 1, 6, 2, true>(tx, tw, tdz, a, st);
         if (C <= 256) return launch_fwd<256, 1, 4, 2, true>(tx, tw, tdz, a, st);

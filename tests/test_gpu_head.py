@@ -64,7 +64,9 @@ def _run(B, K, C, variant, bias, seed=0, unk_weight=1.0):
 
 
 SHAPES = [(64, 2048, 116), (256, 2048, 116), (1024, 2048, 152), (300, 128, 40), (130, 64, 2), (129, 192, 250),
-          (512, 1024, 300), (200, 256, 512), (384, 256, 1000), (257, 512, 513), (128, 128, 1024)]
+          (512, 1024, 300), (200, 256, 512), (384, 256, 1000), (257, 512, 513), (128, 128, 1024),
+          # split-K forward (B <= 2048, C <= 256, K >= 512): one k-block per CTA, uneven k split, ragged rows and columns
+          (2048, 512, 250), (100, 576, 33), (1500, 1024, 256), (2047, 640, 5)]
 
 
 @pytest.mark.parametrize("B,K,C", SHAPES)
@@ -101,6 +103,36 @@ def test_head_single_cta_kernels_vs_oracle(B, K, C):
     assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
     assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < DW_TOL
     assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+
+
+@pytest.mark.parametrize("B,K,C", [(64, 2048, 116), (1024, 2048, 152), (777, 1024, 200)])
+@pytest.mark.parametrize("variant", ["entropic", "garbage", "softmax"])
+def test_head_small_batch_splitk_vs_persistent_forward(B, K, C, variant):
+    """Small batches take the split-K forward (cluster of 8 CTAs, reduce-scatter through distributed shared memory).
+    The persistent kernel stays reachable through a developer switch: both must match the oracle (bias, valid-column
+    maximum of the garbage variant, ignored rows of the softmax variant) and agree with each other."""
+    from openset_imagenet_b200 import _lib as L
+    out = {}
+    for on in (1, 0):
+        L.load().osb_debug_set_head_splitk(on)
+        try:
+            head, loss, xt, ref, (x, W, b, y) = _run(B, K, C, variant, bias=True, seed=B + C + 3)
+        finally:
+            L.load().osb_debug_set_head_splitk(1)
+        assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
+        assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
+        assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < 8e-3
+        assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+        vc = C - 1 if variant == "garbage" else C
+        pt, pm, pred = O.row_stats(ref["logits"], y, vc)
+        st = head.last_stats
+        np.testing.assert_allclose(st.p_target.cpu().numpy(), pt, rtol=2e-3, atol=1e-6)
+        np.testing.assert_allclose(st.p_max.cpu().numpy(), pm, rtol=2e-3, atol=1e-6)
+        assert np.mean(st.pred.cpu().numpy() == pred) > 0.999
+        out[on] = (float(loss), st.p_target.cpu().numpy(), xt.grad.float().cpu().numpy())
+    assert out[1][0] == pytest.approx(out[0][0], rel=1e-5)
+    np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-4, atol=1e-7)
+    assert _rel(out[1][2], out[0][2]) < 6e-3      # two bf16 roundings of dZ and dX apart
 
 
 def test_head_many_tiles_per_cta_pair():

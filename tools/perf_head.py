@@ -60,7 +60,9 @@ def head_case(B, K, C, variant="entropic"):
         lib.osb_debug_set_head_pairs(0); bdw(); lib.osb_debug_set_head_pairs(1)
     def fwd1():
         lib.osb_debug_set_head_pairs(0); fwd(); lib.osb_debug_set_head_pairs(1)
-    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd 1-CTA", fwd1, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dx 1-CTA", bdx1, fl),
+    def fwd_persist():
+        lib.osb_debug_set_head_splitk(0); fwd(); lib.osb_debug_set_head_splitk(1)
+    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd persistent", fwd_persist, fl), ("fwd 1-CTA", fwd1, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dx 1-CTA", bdx1, fl),
                         ("dw(K3+reduce)", bdw, fl), ("dw 1-CTA", bdw1, fl), ("dw GEMM only", bdwp, fl), ("step", step, 3 * fl)]:
         med, mn = timeit(fn)
         med2, mn2 = timeit(fn, flush_l2=False)
@@ -113,6 +115,8 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "head"):
         head_case(16384, 2048, 1000)
+    if which in ("all", "head", "small"):
+        head_case(2048, 2048, 152, "garbage")
         head_case(1024, 2048, 152, "garbage")
         head_case(256, 2048, 116)
         head_case(64, 2048, 116)
