@@ -216,8 +216,13 @@ def run_head(args, cfg, rank, world, dev, peaks):
     value = world * B / (ms_per_step * 1e-3)
 
     # per-kernel times: a second, shorter loop with events between the launches (kept out of the headline loop)
-    n_ev = max(10, min(args.steps, 100))
+    # The GPU first spins for ~10 ms so that the host has every launch and event of this loop queued before the
+    # first kernel starts: the events then bracket kernels that run back to back, not the host's launch gaps.
+    n_ev = max(10, min(args.steps, 50))
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
+    torch.cuda.synchronize()
+    if world == 1:
+        torch.cuda._sleep(20_000_000)
     for i in range(n_ev):
         step(i, evs[i])
     torch.cuda.synchronize()

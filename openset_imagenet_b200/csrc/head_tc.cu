@@ -1194,6 +1194,10 @@ static_assert(kSkS * (kSkBN / 4) * kSkRows * 16 <= kSkStages * kSkStageBytes, "e
 static_assert(kSkSmemBytes <= 232448, "split-K forward shared memory");
 static_assert(kSkLanes == 8, "the row epilogue reduces over 8 lanes");
 
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void st_peer_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -1221,6 +1225,10 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank_();
     const int tile = (int)(blockIdx.x / kSkS);
+    long long* trace = a.trace ? a.trace + (size_t)blockIdx.x * 64 : nullptr;     // developer hook: phase stamps of this CTA
+    auto stamp = [&](int slot) { if (trace && threadIdx.x == kEpiWarp0 * 32) trace[slot] = gtime(); };
+    stamp(0);
+    if (trace && threadIdx.x == kEpiWarp0 * 32) trace[20] = clock64();
     const int n_kb = (a.K + BK - 1) / BK;
     const int kb0 = n_kb * rank / kSkS, kb1 = n_kb * (rank + 1) / kSkS;
     const bool has_k = kb1 > kb0;
@@ -1235,9 +1243,27 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
     if (warp == 1) tmem_alloc(tmem_slot, kSkBN);
     tc_fence_before_sync();
-    cluster_sync_();
+    __syncthreads();                                                  // nothing remote is touched before the cluster barrier below
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_slot;
+    stamp(1);
+    // The epilogue threads have nothing to do until the MMAs complete: the label of the row a thread will own after the
+    // reduce-scatter, its class weight and the denominator (three dependent global round trips) are fetched now, under
+    // the operand loads.
+    const int te = (int)threadIdx.x - kEpiWarp0 * 32;
+    const int row16 = te / kSkLanes, sub = te % kSkLanes;
+    const int row = tile * BM + rank * kSkRows + row16;
+    const bool row_ok = te >= 0 && row < a.B;
+    int64_t y = -1;
+    RowMode rm; rm.mode = kRowIgnored; rm.omega = 0.f;
+    float inv_den = 0.f;
+    if (te >= 0) {
+        if (row_ok) {
+            y = a.y[row];
+            rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, a.t_uniform * (float)a.C);
+        }
+        inv_den = (float)(1.0 / a.den[0]);
+    }
 
     if (warp == 0) {
         // ------------------------------ TMA producer: this CTA's k-blocks of the X tile and of W ----------------------
@@ -1276,9 +1302,13 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         mbar_wait_warp(t_full, 0);
         tc_fence_after_sync();
     }
+    stamp(2);
     // every MMA of every CTA of the cluster has completed (the epilogue warps arrive after their t_full): the operand
-    // stages of all 8 CTAs are free and become the exchange buffer  [source rank][float4 group][owned row] x 16 bytes
-    cluster_sync_();
+    // stages of all 8 CTAs are free and become the exchange buffer  [source rank][float4 group][owned row] x 16 bytes.
+    // Execution ordering only (the reads it protects are complete): the relaxed arrive spares the MEMBAR.ALL.GPU that
+    // the release form compiles to.
+    cluster_sync_relaxed();
+    stamp(3);
 
     if (warp >= kEpiWarp0) {
         const int q = warp & 3;
@@ -1301,19 +1331,12 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 st_peer_v4(dst0 + (uint32_t)((((c0 >> 2) + i) * kSkRows) * 16), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
     }
+    stamp(4);
     tc_fence_before_sync();
     cluster_sync_();                                                  // partials delivered (release / acquire at cluster scope)
+    stamp(5);
 
     if (warp >= kEpiWarp0) {
-        const int te = threadIdx.x - kEpiWarp0 * 32;
-        const int row16 = te / kSkLanes, sub = te % kSkLanes;
-        const int row = tile * BM + rank * kSkRows + row16;
-        const bool row_ok = row < a.B;
-        const int64_t y = row_ok ? a.y[row] : -1;
-        const float s_uniform = a.t_uniform * (float)a.C;
-        RowMode rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, s_uniform);
-        if (!row_ok) { rm.mode = kRowIgnored; rm.omega = 0.f; }
-        const float inv_den = (float)(1.0 / a.den[0]);
         const float4* rbuf = reinterpret_cast<const float4*>(smem);
         constexpr int NJ = kSkBN / 32;                                // float4 groups per thread, at most
         const int nj = nc4 / kSkLanes;
@@ -1344,6 +1367,7 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 }
             }
         }
+        stamp(6);
         group_argmax<kSkLanes>(m, am);                                // ties go to the smaller column (numpy)
         mv = group_max<kSkLanes>(mv);
         float s = 0.f, sumz = 0.f, zy = 0.f;
@@ -1393,6 +1417,7 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 }
             }
         }
+        stamp(7);
         // ---- per-row outputs and the row's loss term ----
         if (sub == 0) {
             double rl = 0.0;
@@ -1437,9 +1462,12 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             }
         }
     }
+    stamp(8);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tbase, kSkBN);
+    stamp(9);
+    if (trace && threadIdx.x == kEpiWarp0 * 32) trace[21] = clock64();
 }
 
 // ---- host --------------------------------------------------------------------------------------

@@ -210,6 +210,9 @@ extern "C" int osb_label_stats(const int64_t* y, const float* class_w, int64_t B
     OSB_REQUIRE(ws_bytes >= osb_loss_workspace_bytes(B), OSB_ERR_WORKSPACE, "osb_label_stats: workspace too small");
     int grid = (int)((B + kLabelThreads - 1) / kLabelThreads);
     grid = grid < 1 ? 1 : (grid > kMaxReduceGrid ? kMaxReduceGrid : grid);
+    // osb_set_cta_limit bounds this grid too: a caller that runs the statistics beside a GEMM kernel keeps them on a few
+    // SMs (the sums are integers and the row count: the result does not depend on the grid)
+    if (grid > cta_limit()) grid = cta_limit();
     auto* ticket = reinterpret_cast<unsigned int*>(ws);
     auto* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kTicketBytes);
     label_stats_kernel<<<grid, kLabelThreads, 0, (cudaStream_t)stream>>>(y, class_w, B, C, variant, ignore_index,

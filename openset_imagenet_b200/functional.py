@@ -46,6 +46,10 @@ class HeadPlan:
         self.ws = workspace
         self.ws_bytes_needed = ws_bytes
         self.den = torch.empty(1, dtype=torch.float64, device=d)
+        # entropic loss: the denominator is the row count (losses.py:29), known without reading the labels, so a captured
+        # step takes the label statistics off the critical path (own workspace: it may run beside the GEMM kernels)
+        self.den_const = torch.full((1,), float(B), dtype=torch.float64, device=d)
+        self.ws_label = torch.zeros(L.size("osb_loss_workspace_bytes", B) + 256, dtype=torch.uint8, device=d)
         self.label_counts = torch.empty(4, dtype=torch.int64, device=d)
         # [dW | db | loss] may live in one caller-owned float32 buffer (the packed all-reduce buffer of dist.py), so
         # that the kernels write straight into it and no gather copy is needed
@@ -74,15 +78,17 @@ class HeadPlan:
         if y.shape != (self.B,) or y.dtype != torch.int64:
             raise ValueError("y must be int64 [B]")
 
-    def label_stats(self, y, den_scale_hook=None):
+    def label_stats(self, y, den_scale_hook=None, ws=None):
+        ws = self.ws if ws is None else ws
         L.call("osb_label_stats", L.ptr(y), L.ptr(self.class_w), self.B, self.C, self.variant, self.ignore_index,
-               L.ptr(self.den), L.ptr(self.label_counts), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+               L.ptr(self.den), L.ptr(self.label_counts), L.ptr(ws), ws.numel(), L.stream_ptr(self.dev))
         if den_scale_hook is not None:
             den_scale_hook(self.den)
 
-    def forward(self, x, w, y, bias=None, write_dz=True, want_pred=True):
+    def forward(self, x, w, y, bias=None, write_dz=True, want_pred=True, den=None):
         L.call("osb_head_forward", L.ptr(x), self.K, L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(self.class_w),
-               self.B, self.K, self.C, self.variant, self.unk_weight, self.ignore_index, L.ptr(self.den), self.valid_cols,
+               self.B, self.K, self.C, self.variant, self.unk_weight, self.ignore_index,
+               L.ptr(self.den if den is None else den), self.valid_cols,
                L.ptr(self.loss_num), L.ptr(self.loss), L.ptr(self.p_target), L.ptr(self.p_max),
                L.ptr(self.p_max_all) if want_pred else None, L.ptr(self.pred) if want_pred else None,
                L.ptr(self.dz) if write_dz else None, self.lddz,
@@ -108,24 +114,49 @@ class HeadPlan:
         # dZ, so they become parallel branches of the graph.  Large batches fill the GPU with either kernel and stay serial.
         fork = self.B <= 4096 if parallel_backward is None else bool(parallel_backward)
         branch = torch.cuda.Stream(device=self.dev) if fork else None
+        # Entropic loss: the forward kernel takes the constant denominator and the label statistics (counts for the
+        # caller, the same denominator) become a branch beside the backward kernels instead of the first link of the chain.
+        side_labels = self.variant == L.ENTROPIC
+        lbranch = torch.cuda.Stream(device=self.dev) if side_labels else None
+
+        def labels_beside():
+            # at most 8 CTAs: next to the dW GEMM (64 CTA pairs on 74 SM pairs at the large configuration) they take
+            # SMs nobody else wants, whichever kernel the hardware places first
+            lbranch.wait_stream(side)
+            with torch.cuda.stream(lbranch):
+                lib = L.load()
+                lib.osb_set_cta_limit(8)
+                try:
+                    self.label_stats(y, ws=self.ws_label)
+                finally:
+                    lib.osb_set_cta_limit(0)
 
         def body():
-            if not fork:
-                self.step(x, w, y, bias, gscale)
-                return
-            self.label_stats(y)
-            self.forward(x, w, y, bias, want_pred=False)
-            branch.wait_stream(side)
-            with torch.cuda.stream(branch):
+            if not side_labels:
+                self.label_stats(y)
+            self.forward(x, w, y, bias, want_pred=False, den=self.den_const if side_labels else None)
+            if fork:
+                if side_labels:
+                    labels_beside()
+                branch.wait_stream(side)
+                with torch.cuda.stream(branch):
+                    self.backward_dw(x, w, gscale)
+                self.backward_dx(x, w, gscale)
+                side.wait_stream(branch)
+            else:
+                self.backward_dx(x, w, gscale)
+                if side_labels:
+                    labels_beside()
                 self.backward_dw(x, w, gscale)
-            self.backward_dx(x, w, gscale)
-            side.wait_stream(branch)
+            if side_labels:
+                side.wait_stream(lbranch)
 
         with torch.cuda.stream(side):
             body()                                           # warm-up outside capture (function attributes, descriptors)
             side.synchronize()
-            if branch is not None:
-                branch.synchronize()
+            for b_ in (branch, lbranch):
+                if b_ is not None:
+                    b_.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 body()
