@@ -142,12 +142,12 @@ def run_head(args, cfg, rank, world, dev, peaks):
     allreduce = "none"
     if world > 1:
         try:            # dW all-reduce over NVLink peer memory, fused with the split-K reduction (no NCCL on the data path)
-            sp = ShardedHeadPlan(B, K, C, cfg["variant"], peer_allreduce=True, sm_reserve=32, **plan_kw)
+            sp = ShardedHeadPlan(B, K, C, cfg["variant"], peer_allreduce=True, sm_reserve=args.sm_reserve, **plan_kw)
             allreduce = "peer-memory kernel fused with the split-K reduction (osb_head_dw_allreduce), overlapped with dX"
         except Exception as e:                                  # no symmetric memory on this box: NCCL all-reduce
             if rank == 0:
                 print(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-            sp = ShardedHeadPlan(B, K, C, cfg["variant"], sm_reserve=32, **plan_kw)
+            sp = ShardedHeadPlan(B, K, C, cfg["variant"], sm_reserve=args.sm_reserve, **plan_kw)
             allreduce = "NCCL all-reduce of the packed fp32 [dW | loss] buffer, overlapped with dX"
     else:
         sp = ShardedHeadPlan(B, K, C, cfg["variant"], **plan_kw)
@@ -159,9 +159,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
         if ev is None:
             sp.finish(sp.step(x, w, y))
             return
-        plan.label_stats(y, sp._den_hook)
-        ev[0].record()
-        plan.forward(x, w, y, want_pred=False)
+        late_labels = sp.begin(x, w, y, mark=ev[0].record)      # (label statistics ->) forward; see ShardedHeadPlan.begin
         ev[1].record()
         if sp.peer is not None:
             plan.backward_dw_partials(x)
@@ -177,6 +175,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
         if world > 1:
             sp._L.load().osb_set_cta_limit(0)
         ev[3].record()
+        sp.end(y, late_labels)
         sp.finish(work)
 
     # One GPU: the five launches of a step are replayed from a CUDA graph (one graph per rotating input buffer), so
@@ -525,6 +524,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph (N=1)")
     ap.add_argument("--no-oscr", action="store_true")
+    ap.add_argument("--sm-reserve", type=int, default=32, help="SMs left to the gradient all-reduce while dX runs (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()

@@ -199,6 +199,7 @@ class ShardedHeadPlan:
         self._L = L
         self._sms = L.size("osb_sm_count")
         self.sm_reserve = int(sm_reserve) if self.world > 1 else 0
+        self._den_global = None
         self.launches_per_step = self.plan.launches_per_step      # our kernels only (the collective is NCCL's)
 
     def _den_hook(self, den):
@@ -214,8 +215,7 @@ class ShardedHeadPlan:
         current stream wait for it.  After that ``plan.dw`` / ``plan.db`` hold the full-batch gradients and
         ``plan.loss`` the full-batch loss on every rank; ``plan.dx`` is this shard's d loss / d features."""
         p = self.plan
-        p.label_stats(y, self._den_hook)
-        p.forward(x, w, y, bias, want_pred=False)       # training step: no per-row predictions (HeadPlan.step)
+        late_labels = self.begin(x, w, y, bias)
         if self.peer is not None:
             p.backward_dw_partials(x)
             done = self.peer.run()
@@ -224,6 +224,7 @@ class ShardedHeadPlan:
                 p.backward_dx(x, w)
             finally:
                 self._L.load().osb_set_cta_limit(0)
+            self.end(y, late_labels)
             return done
         p.backward_dw(x, w)
         work = None
@@ -235,7 +236,29 @@ class ShardedHeadPlan:
         finally:
             if self.world > 1:
                 self._L.load().osb_set_cta_limit(0)
+        self.end(y, late_labels)
         return work
+
+    def begin(self, x, w, y, bias=None, mark=None) -> bool:
+        """Label statistics + forward.  The entropic loss divides by the global row count (every row counts, shards are
+        equal), known without reading the labels: the forward kernel takes that constant and the statistics kernel
+        (counts for the caller, the same denominator) moves behind the GEMMs (``end``), off the head of the dependency
+        chain.  The softmax / garbage variants need the all-reduced sum of weights first.  Returns whether ``end`` has
+        the statistics left to do.  ``mark`` (bench.py) is called right before the forward launch."""
+        p = self.plan
+        late = self.variant == "entropic"
+        if late and self._den_global is None:
+            self._den_global = torch.full((1,), float(p.B * self.world), dtype=torch.float64, device=p.dev)
+        if not late:
+            p.label_stats(y, self._den_hook)
+        if mark is not None:
+            mark()
+        p.forward(x, w, y, bias, want_pred=False, den=self._den_global if late else None)   # training step: no per-row predictions
+        return late
+
+    def end(self, y, late_labels: bool) -> None:
+        if late_labels:
+            self.plan.label_stats(y, self._den_hook, ws=self.plan.ws_label)
 
     def finish(self, work):
         """Make the current stream wait for the gradient all-reduce.  With the peer-memory path the full-batch loss
