@@ -165,30 +165,40 @@ def test_head_many_tiles_garbage_variant_with_bias():
     assert np.mean(st.pred.cpu().numpy() == pred) > 0.999
 
 
-@pytest.mark.parametrize("B", [300, 5000])
-def test_head_plan_graph_replay_matches_eager_step(B):
-    """HeadPlan.capture (dX and dW as parallel graph branches for small batches, serial for large ones) reproduces the
-    eager step bit for bit: the kernels are deterministic and the graph only changes how they are launched."""
+@pytest.mark.parametrize("B,K,C,variant", [(300, 256, 300, "entropic"), (5000, 256, 300, "entropic"),
+                                             (1024, 2048, 152, "entropic"), (1024, 2048, 152, "garbage")])
+def test_head_plan_graph_replay_matches_eager_step(B, K, C, variant):
+    """HeadPlan.capture (dX and dW as parallel graph branches for small batches, serial for large ones; for the entropic
+    loss the label statistics as one more branch, with the row count as the forward kernel's denominator) reproduces the
+    eager step bit for bit, label counts and denominator included: the kernels are deterministic and the graph only
+    changes how they are launched.  The 1024-row cases take the split-K forward."""
     from openset_imagenet_b200.functional import HeadPlan
-    K, C = 256, 300
     dev = torch.device(DEV)
     g = torch.Generator(device=dev).manual_seed(B)
     x = torch.randn(B, K, device=dev, generator=g).bfloat16()
     w = (torch.randn(C, K, device=dev, generator=g) / K ** 0.5).bfloat16()
-    y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=3), device=dev)
-    plan = HeadPlan(B, K, C, "entropic", device=dev)
+    if variant == "garbage":
+        yn = O.make_labels(B, C - 1, 1 / 3, seed=3, neg_label=C - 1)
+        cw = torch.tensor(O.class_weights_from_labels(np.concatenate([yn, np.arange(C)]), C), device=dev)
+        plan = HeadPlan(B, K, C, "garbage", class_weights=cw, last_valid_class=-1, device=dev)
+    else:
+        yn = O.make_labels(B, C, 1 / 3, seed=3)
+        plan = HeadPlan(B, K, C, "entropic", device=dev)
+    y = torch.tensor(yn, device=dev)
+    outs = lambda: (plan.loss, plan.dx, plan.dw, plan.p_target, plan.p_max, plan.den, plan.label_counts)
     plan.step(x, w, y)
     torch.cuda.synchronize()
-    ref = [t.clone() for t in (plan.loss, plan.dx, plan.dw, plan.p_target, plan.p_max)]
-    for t in (plan.loss, plan.dx, plan.dw, plan.p_target, plan.p_max):
-        t.zero_()
+    ref = [t.clone() for t in outs()]
     graph = plan.capture(x, w, y)
-    for t in (plan.loss, plan.dx, plan.dw):
+    for t in outs():
         t.zero_()
-    graph.replay()
+    for _ in range(3):                      # replays reuse the workspace (tickets, exchange epochs) left by the previous one
+        graph.replay()
     torch.cuda.synchronize()
-    for got, want in zip((plan.loss, plan.dx, plan.dw, plan.p_target, plan.p_max), ref):
+    for got, want in zip(outs(), ref):
         assert torch.equal(got, want)
+    n_neg = int((yn < 0).sum()) if variant == "entropic" else 0
+    assert plan.label_counts.tolist()[:2] == [B - n_neg, n_neg]
 
 
 @pytest.mark.parametrize("B,K,C", [(256, 2048, 116), (200, 256, 300), (384, 256, 1000)])
