@@ -122,6 +122,12 @@ int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bia
                      double* loss_num, float* loss,
                      float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
                      void* dz, int64_t lddz, void* ws, size_t ws_bytes, void* stream);
+/* osb_head_forward_after_labels(1): the caller promises that, on the stream of its next osb_head_forward calls, the
+ * kernel directly in front of the forward is osb_label_stats (train.py:135: the loss follows the logits of the same batch,
+ * so the features are complete before the label statistics start).  Small batches (the split-K forward) are then launched
+ * with programmatic stream serialization: operands are loaded and multiplied while the statistics still run, and the kernel
+ * waits for them before it reads `den`.  Thread-local; returns the previous setting; 0 restores plain stream order. */
+int osb_head_forward_after_labels(int on);
 int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
                       int64_t B, int K, int C, const float* gscale,
                       void* dx, int64_t lddx, float* dw, float* db,

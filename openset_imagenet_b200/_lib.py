@@ -36,6 +36,7 @@ SIGNATURES = {
     "osb_head_workspace_bytes": (_sz, [_i64, _i, _i]),
     "osb_head_forward": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _i64, _p, _i,
                               _p, _p, _p, _p, _p, _p, _p, _i64, _p, _sz, _p]),
+    "osb_head_forward_after_labels": (_i, [_i]),
     "osb_head_backward": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "osb_head_dw_partials_offset": (_sz, []),
     "osb_head_dw_splits": (_i, [_i64, _i, _i]),

@@ -46,6 +46,12 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 }
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Programmatic dependent launch.  A kernel launched with programmatic stream serialization starts once every CTA of the
+// kernel in front of it has called pdl_trigger (or exited) and runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch) under that kernel's tail; pdl_wait returns when the kernel in front has completed and its writes are visible.
+// Both are no-ops in a plain launch.  Nothing global is read or written before pdl_wait.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- cluster helpers (2-CTA class split) -------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -949,6 +955,8 @@ head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();                 // dZ comes from the forward kernel in front of this one
+    pdl_trigger();              // the split-K reduce behind it may be scheduled
     const uint32_t tbase = *tmem_slot;
     const int n_tiles = (K + kDwBN - 1) / kDwBN;
     const int unit = blockIdx.x;
@@ -1052,6 +1060,8 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     tc_fence_before_sync();
     cluster_sync_();
     tc_fence_after_sync();
+    pdl_wait();                 // dZ comes from the forward kernel in front of this one
+    pdl_trigger();              // the split-K reduce behind it may be scheduled
     const uint32_t tbase = *tmem_slot;
     const int n_tiles = (K + kDwBN - 1) / kDwBN;
     const int unit = blockIdx.x >> 1;
@@ -1142,6 +1152,7 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 __global__ void __launch_bounds__(256)
 dw_reduce_kernel(const float4* __restrict__ partials, int splits, size_t n4, const float* __restrict__ gscale,
                  float4* __restrict__ dw) {
+    pdl_wait();                 // the partials come from the dW GEMM in front of this kernel
     const float gs = gscale ? gscale[0] : 1.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 acc = partials[i];
@@ -1247,6 +1258,7 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_slot;
     stamp(1);
+    pdl_trigger();              // the dW GEMM behind this kernel may set itself up; it waits for dZ (pdl_wait) before it loads
     // The epilogue threads have nothing to do until the MMAs complete: the label of the row a thread will own after the
     // reduce-scatter, its class weight and the denominator (three dependent global round trips) are fetched now, under
     // the operand loads.
@@ -1262,6 +1274,10 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             y = a.y[row];
             rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, a.t_uniform * (float)a.C);
         }
+        // Launched with programmatic stream serialization right behind label_stats_kernel (osb_head_forward_after_labels),
+        // this grid starts while that one still runs: the TMA and MMA warps only read the caller's inputs, and the epilogue
+        // warps wait here, before the denominator and long before anything is written (a no-op in a plain launch).
+        pdl_wait();
         inv_den = (float)(1.0 / a.den[0]);
     }
 
@@ -1559,6 +1575,11 @@ using namespace osb::head;
 
 // developer hook (not part of the public header): A/B switch between the single-CTA and the CTA-pair kernels
 extern "C" void osb_debug_set_head_pairs(int on) { g_head_pairs = on; }
+// osb_head_forward_after_labels(1): the caller promises that the kernel in front of the next osb_head_forward calls on
+// their stream is osb_label_stats (whose own predecessor has completed): the split-K forward is then launched with
+// programmatic stream serialization and loads its operands while the label statistics still run.
+static thread_local int g_fwd_after_labels = 0;
+extern "C" int osb_head_forward_after_labels(int on) { const int old = g_fwd_after_labels; g_fwd_after_labels = on ? 1 : 0; return old; }
 // developer hook: 0 sends small batches through the persistent kernels too (A/B reference of the split-K forward)
 static int g_head_splitk = 1;
 extern "C" void osb_debug_set_head_splitk(int on) { g_head_splitk = on; }
@@ -1596,6 +1617,17 @@ static int g_dbg = 0;
 extern "C" void osb_debug_set_head_dbg(int v) { g_dbg = v; }
 // developer hook (not part of the public header): device buffer of [grid][64] int64 clock stamps, or NULL
 extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<long long*>(p); }
+
+// launch configuration with programmatic stream serialization: the kernel's prologue may overlap the tail of the kernel in
+// front of it on the stream; the kernel itself calls pdl_wait before it touches anything that kernel produces
+static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr->val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cfg;
+}
 
 extern "C" size_t osb_head_workspace_bytes(int64_t B, int K, int C) {
     if (B < 0 || K <= 0 || C <= 0) return 0;
@@ -1660,15 +1692,24 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.xch_stats = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + kWsOffStats);
     a.trace = g_trace;
     if (splitk) {
-        const int grid = (int)((B + BM - 1) / BM) * kSkS;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((B + BM - 1) / BM) * kSkS);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSkSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_fwd_after_labels ? 1 : 0;      // the cluster shape is a compile-time attribute of the kernel
+        __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dz);
         if (bias) {
             rc = set_smem(head_fwd_splitk_kernel<true>, kSkSmemBytes); if (rc) return rc;
-            head_fwd_splitk_kernel<true><<<grid, kThreads, kSkSmemBytes, st>>>(tx, tw, a, reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_fwd_splitk_kernel<true>, tx, tw, a, dzp, lddz));
         } else {
             rc = set_smem(head_fwd_splitk_kernel<false>, kSkSmemBytes); if (rc) return rc;
-            head_fwd_splitk_kernel<false><<<grid, kThreads, kSkSmemBytes, st>>>(tx, tw, a, reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_fwd_splitk_kernel<false>, tx, tw, a, dzp, lddz));
         }
-        OSB_LAUNCH_CHECK();
         return OSB_OK;
     }
     if (pair) {
@@ -1729,28 +1770,30 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
         OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
         const int splits = dw_splits((int)B, K, C);
         float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
+        cudaLaunchAttribute pdl_attr;
         if (dw_pairs(C)) {
             rc = set_smem(head_dw2_kernel, kDw2SmemBytes);
             if (rc) return rc;
             const int units = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN) * splits;
             CUtensorMap tpart;
             OSB_TMAP(make_tmap_f32_3d(&tpart, partials, (uint64_t)splits, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW partials (store)");
-            head_dw2_kernel<<<units * 2, kThreads, kDw2SmemBytes, st>>>(tdz, tx, tpart, (int)B, K, C, splits, g_trace);
+            cudaLaunchConfig_t cfg = pdl_config(dim3(units * 2), dim3(kThreads), kDw2SmemBytes, st, &pdl_attr);
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, (int)B, K, C, splits, g_trace));
         } else {
             rc = set_smem(head_dw_kernel, kDwSmemBytes);
             if (rc) return rc;
             const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
-            head_dw_kernel<<<units, kThreads, kDwSmemBytes, st>>>(tdz, tx, (int)B, K, C, splits, partials);
+            cudaLaunchConfig_t cfg = pdl_config(dim3(units), dim3(kThreads), kDwSmemBytes, st, &pdl_attr);
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw_kernel, tdz, tx, (int)B, K, C, splits, partials));
         }
-        OSB_LAUNCH_CHECK();
         if (dw) {
             const size_t n4 = (size_t)C * K / 4;
             int rgrid = (int)((n4 + 255) / 256);
             const int cap = sm_count() * 8;
             if (rgrid > cap) rgrid = cap;
-            dw_reduce_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(partials), splits, n4, gscale,
-                                                    reinterpret_cast<float4*>(dw));
-            OSB_LAUNCH_CHECK();
+            cudaLaunchConfig_t cfg = pdl_config(dim3(rgrid), dim3(256), 0, st, &pdl_attr);
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, dw_reduce_kernel, reinterpret_cast<const float4*>(partials), splits, n4, gscale,
+                                        reinterpret_cast<float4*>(dw)));
         }
     }
     if (db) {

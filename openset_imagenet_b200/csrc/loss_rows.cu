@@ -18,6 +18,9 @@ __global__ void __launch_bounds__(kLabelThreads)
 label_stats_kernel(const int64_t* __restrict__ y, const float* __restrict__ class_w, int64_t B, int C,
                    int variant, int64_t ignore_index, double* __restrict__ den_out,
                    int64_t* __restrict__ counts_out, double* partials, unsigned int* ticket) {
+    // A forward kernel launched with programmatic stream serialization (osb_head_forward_after_labels) may start its
+    // operand loads now; it waits for this grid (griddepcontrol.wait) before it reads the denominator.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     double den = 0.0;
     long long c_onehot = 0, c_uniform = 0, c_ignored = 0, c_bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {

@@ -133,15 +133,25 @@ class HeadPlan:
 
         def body():
             if not side_labels:
+                # the forward kernel may start under the label statistics it follows (osb_head_forward_after_labels)
                 self.label_stats(y)
-            self.forward(x, w, y, bias, want_pred=False, den=self.den_const if side_labels else None)
+                lib = L.load()
+                lib.osb_head_forward_after_labels(1)
+                try:
+                    self.forward(x, w, y, bias, want_pred=False)
+                finally:
+                    lib.osb_head_forward_after_labels(0)
+            else:
+                self.forward(x, w, y, bias, want_pred=False, den=self.den_const)
             if fork:
                 if side_labels:
                     labels_beside()
+                # dX on the branch; the longer chain (dW GEMM + split-K reduce) stays on the stream of the forward kernel,
+                # where each kernel is launched programmatically behind the one in front of it
                 branch.wait_stream(side)
                 with torch.cuda.stream(branch):
-                    self.backward_dw(x, w, gscale)
-                self.backward_dx(x, w, gscale)
+                    self.backward_dx(x, w, gscale)
+                self.backward_dw(x, w, gscale)
                 side.wait_stream(branch)
             else:
                 self.backward_dx(x, w, gscale)
