@@ -60,8 +60,9 @@ int         osb_abi_version(void);
 const char* osb_last_error(void);            /* host string, valid until the next failing call on this thread */
 int         osb_device_check(void);          /* OSB_OK iff the current device is compute capability 10.x */
 int         osb_sm_count(void);              /* SM count of the current device (148 on B200), <0 on error */
-/* Upper bound on the grid of the persistent head kernels (forward, dX); 0 = one CTA per SM (default).  Set it to
- * SMs - k while a collective runs beside them so that the collective's CTAs find free SMs.  Returns the old value. */
+/* Upper bound on the grid of the persistent head kernels (forward, dX) and of osb_label_stats; 0 = one CTA per SM
+ * (default).  Set it to SMs - k while a collective runs beside them so that the collective's CTAs find free SMs, or to a
+ * handful while the label statistics run beside a GEMM.  Returns the old value. */
 int         osb_set_cta_limit(int max_ctas);
 
 /* ---- labels -> denominator and counts ------------------------------------------------------ *
