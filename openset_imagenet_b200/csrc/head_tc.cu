@@ -254,6 +254,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (PAIR) cluster_sync_(); else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_slot;
+    pdl_trigger();              // the backward GEMM behind this kernel may set itself up on SMs this grid leaves idle or has left
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -805,6 +806,8 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     tc_fence_before_sync();
     cluster_sync_();
     tc_fence_after_sync();
+    pdl_wait();                 // dZ comes from the kernel in front of this one
+    pdl_trigger();
     const uint32_t tbase = *tmem_slot;
     const int m_tiles = (B + 255) / 256, n_tiles = (K + kDxBN - 1) / kDxBN;
     const int total = m_tiles * n_tiles;
@@ -1625,7 +1628,9 @@ static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr->val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    // developer switch for A/B measurements: OSB_NO_PDL=1 launches in plain stream order
+    static const bool no_pdl = getenv("OSB_NO_PDL") != nullptr;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
     return cfg;
 }
 
@@ -1752,8 +1757,9 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
             const int total2 = (int)((B + 255) / 256) * ((K + kDxBN - 1) / kDxBN);
             int pairs = cta_limit() / 2;
             if (pairs > total2) pairs = total2;
-            head_dx2_kernel<<<pairs * 2, kDx2Threads, kDx2SmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale, g_trace, g_dbg);
-            OSB_LAUNCH_CHECK();
+            cudaLaunchAttribute pdl_attr;
+            cudaLaunchConfig_t cfg = pdl_config(dim3(pairs * 2), dim3(kDx2Threads), kDx2SmemBytes, st, &pdl_attr);
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel, tdz, tw, tdx, (int)B, K, C, gscale, g_trace, g_dbg));
         } else {
             rc = set_smem(head_dx_kernel, kDxSmemBytes);
             if (rc) return rc;
