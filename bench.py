@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the B200-native open-set head + OSCR path (contract: see the task statement / DESIGN.md §6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload head|bg|oscr]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload head|bg|oscr|resnet]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -9,13 +9,17 @@ Default workload ("head") = BASELINE.json's large-head configuration, the larges
 the one its tensor-core target is quoted on: entropic open-set loss over a 2048 -> 1000 head on 16384
 bf16 feature rows PER GPU (1/3 negatives), forward + backward (loss, confidence statistics, dX, dW).
 A "step" is one such pass; with N GPUs the batch is sharded (weak scaling: 16384 rows per GPU) and the fp32
-dW (+loss) buffer is all-reduced with NCCL every step.  The same JSON line carries an "oscr" object: OSCR
-over 1M x 116 synthetic scores (BASELINE.json's second headline metric), sharded by rows for N > 1.
+dW (+loss) is all-reduced over NVLink peer memory every step, the whole sharded step replayed from ONE CUDA graph.
+The same JSON line carries sub-objects for the other BASELINE configurations: "oscr" (OSCR over 1M x 116 synthetic
+scores, the second headline metric, sharded by rows for N > 1), "bg" (garbage-class head, Protocol 3 shape) and, at
+N = 1, "resnet" (ResNet-50 + fused head training step).
 
 One JSON line is printed by rank 0.  `value` is device throughput with inputs resident in HBM; `e2e` is
-the same step driven through the C ABI from pinned HOST buffers (H2D of features+labels, D2H of loss, dX
-and dW inside the timed region).  `--impl reference` times the CPU port of the reference's own path
-(oracle/ref_port.py) on the host cores, on a bounded sample of the same workload.
+the same step driven through the C ABI from pinned HOST buffers (H2D of features + labels and D2H of the loss inside
+the timed region; dX and dW stay on the device for the backbone / optimiser).  `parity.head` compares the benchmarked
+kernels with the float64 oracle on a sub-batch (and, for N > 1, the all-reduced dW across ranks and against one GPU).
+`--impl reference` times the reference's OWN files (losses.py, metrics.py: vendored verbatim into oracle/_ref by
+oracle/vendor_ref.py) on the host cores, on the same configuration.
 """
 from __future__ import annotations
 
@@ -88,7 +92,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.0005)               # NVML answers in ~0.1 ms: >= 1 kHz sampling
 
     def __enter__(self):
         if self.nv is not None:
@@ -104,6 +108,15 @@ class ClockSampler:
     def summary(self):
         return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
                 "samples": len(self.samples), "reasons": sorted(self.reasons)}
+
+
+def pick_tensor_peak(peaks, clocks):
+    """The cuBLAS bf16 peak a tensor-bound measurement is divided by, chosen from the clock record of the SAME region:
+    a power-capped region (sw_power_cap seen) is compared with the sustained figure, anything else with the burst one."""
+    capped = "sw_power_cap" in (clocks or {}).get("reasons", [])
+    kind = "sustained" if capped else "burst"
+    return (peaks["tc_sustained"] if capped else peaks["tc_burst"]), \
+        f"{peaks['src']} cuBLAS bf16 {kind} ({'sw_power_cap seen' if capped else 'no power cap'} in this region's clock record)"
 
 
 def dist_env():
@@ -124,21 +137,94 @@ def make_head_inputs(cfg, dev, nbuf, seed):
         ys_np = [O.make_labels(cfg["B"], cfg["C"], cfg["neg_frac"], seed=seed + i) for i in range(nbuf)]
         cw = None
     ys = [torch.tensor(y, device=dev) for y in ys_np]
-    w = (torch.randn(cfg["C"], cfg["K"], device=dev, generator=g) * (1.0 / cfg["K"] ** 0.5)).bfloat16()
+    # the same weights on every rank (data parallel): their own generator
+    gw = torch.Generator(device=dev).manual_seed(4321)
+    w = (torch.randn(cfg["C"], cfg["K"], device=dev, generator=gw) * (1.0 / cfg["K"] ** 0.5)).bfloat16()
     return xs, ys, ys_np, w, cw
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def head_parity(cfg, x, w, y_np, cw, plan_kw, rows):
+    """The benchmarked kernels (same precision mode, same dX dtype) on the first `rows` rows of a bench buffer against the
+    float64 oracle: relative error of the loss, dW (norm-wise), dX.  A bf16 dX is compared with the oracle ROUNDED to its
+    storage format, and once more as the fp32 accumulator (dx_dtype float32).  The one place the oracle is used here."""
+    from openset_imagenet_b200.functional import HeadPlan
+    from oracle import oracle as O
+    K, C = cfg["K"], cfg["C"]
+    dev = x.device
+    rows = min(rows, x.shape[0])
+    xs, ys = x[:rows].contiguous(), torch.tensor(y_np[:rows], device=dev)
+    ov = {"entropic": O.ENTROPIC, "softmax": O.SOFTMAX, "garbage": O.GARBAGE}[cfg["variant"]]
+    ref = O.head_fwd_bwd(xs.float().cpu().numpy(), w.float().cpu().numpy(), None, y_np[:rows], ov,
+                         class_weights=None if cw is None else cw.cpu().numpy())
+    out = {"rows": rows, "tolerance": 1e-3, "oracle": "oracle/oracle.py head_fwd_bwd (float64) on the bf16 operands the kernels read"}
+    for tag, dt in (("", torch.bfloat16), ("_f32", torch.float32)):
+        plan = HeadPlan(rows, K, C, cfg["variant"], dx_dtype=dt, **plan_kw)
+        plan.step(xs, w, ys)
+        torch.cuda.synchronize()
+        if not tag:
+            out["precision"] = "exact (grad-logits as a bf16 pair)" if plan.planes == 2 else "fast (one bf16 plane of grad-logits)"
+            out["loss_rel"] = abs(float(plan.loss) - ref["loss"]) / abs(ref["loss"])
+            out["dw_rel"] = _rel(plan.dw.cpu().numpy(), ref["dw"])
+            out["dx_bf16_rel_vs_bf16_oracle"] = _rel(plan.dx.float().cpu().numpy(), O.bf16_round(ref["dx"].astype(np.float32)))
+        else:
+            out["dx_f32_rel"] = _rel(plan.dx.cpu().numpy(), ref["dx"])
+    out["ok"] = bool(out["loss_rel"] < 1e-3 and out["dw_rel"] < 1e-3 and out["dx_f32_rel"] < 1e-3)
+    return out
+
+
+def sharded_parity(cfg, sp, x, w, y, plan_kw, rank, world, dev):
+    """N > 1: one more step on buffer 0, then (i) the all-reduced dW / loss must be bit-identical on every rank and (ii)
+    equal, within fp32 summation-order noise, to ONE GPU's dW / loss on the concatenated batch."""
+    import torch.distributed as dist
+    from openset_imagenet_b200.functional import HeadPlan
+    sp.finish(sp.step(x, w, y))
+    torch.cuda.synchronize()
+    sp.check()
+    dw = sp.plan.dw.detach().clone()
+    loss = sp.full_loss().reshape(1).clone()
+    sig = torch.cat([dw.view(torch.int32).sum(dtype=torch.int64).reshape(1), dw.double().abs().sum().view(torch.int64).reshape(1),
+                     loss.view(torch.int64)])
+    sigs = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    identical = all(torch.equal(sigs[0], s_) for s_ in sigs)
+    xs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+    ys = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
+    dist.gather(x, xs, dst=0)
+    dist.gather(y, ys, dst=0)
+    out = {"dw_and_loss_bit_identical_across_ranks": bool(identical)}
+    if rank == 0:
+        big = HeadPlan(cfg["B"] * world, cfg["K"], cfg["C"], cfg["variant"], **plan_kw)
+        big.step(torch.cat(xs), w, torch.cat(ys))
+        torch.cuda.synchronize()
+        out["dw_rel_vs_single_gpu_concatenated_batch"] = _rel(dw.cpu().numpy(), big.dw.cpu().numpy())
+        out["loss_rel_vs_single_gpu_concatenated_batch"] = abs(float(loss) - float(big.loss)) / abs(float(big.loss))
+        out["tolerance"] = 1e-5
+        out["ok"] = bool(identical and out["dw_rel_vs_single_gpu_concatenated_batch"] < 1e-5
+                         and out["loss_rel_vs_single_gpu_concatenated_batch"] < 1e-5)
+        del big
+    dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_head(args, cfg, rank, world, dev, peaks):
+def run_head(args, cfg, rank, world, dev, peaks, light=False):
+    """light: sub-object mode (no e2e, no per-kernel loop): throughput + parity only."""
     import torch.distributed as dist
+    from openset_imagenet_b200 import _lib as L
     from openset_imagenet_b200.dist import ShardedHeadPlan
 
     B, K, C = cfg["B"], cfg["K"], cfg["C"]
     nbuf = 3                                        # 3 x 64 MB of features + 64 MB dX + 32 MB dZ: far larger than the 126 MB L2
     xs, ys, ys_np, w, cw = make_head_inputs(cfg, dev, nbuf, seed=1234 + rank)
-    plan_kw = dict(class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None, device=dev)
+    plan_kw = dict(class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None, device=dev,
+                   precision=cfg.get("precision", "auto"))
     allreduce = "none"
     if world > 1:
         try:            # dW all-reduce over NVLink peer memory, fused with the split-K reduction (no NCCL on the data path)
@@ -153,38 +239,17 @@ def run_head(args, cfg, rank, world, dev, peaks):
         sp = ShardedHeadPlan(B, K, C, cfg["variant"], **plan_kw)
     plan = sp.plan
 
-    def step(i, ev=None):
-        """label stats -> fused forward -> dW -> [all-reduce of dW|loss  overlapped with  dX]"""
-        x, y = xs[i % nbuf], ys[i % nbuf]
-        if ev is None:
-            sp.finish(sp.step(x, w, y))
-            return
-        late_labels = sp.begin(x, w, y, mark=ev[0].record)      # (label statistics ->) forward; see ShardedHeadPlan.begin
-        ev[1].record()
-        if sp.peer is not None:
-            plan.backward_dw_partials(x)
-            ev[2].record()
-            work = sp.peer.run()
-        else:
-            plan.backward_dw(x, w)
-            ev[2].record()
-            work = dist.all_reduce(sp.flat, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
-        if world > 1:
-            sp._L.load().osb_set_cta_limit(sp._sms - sp.sm_reserve)
-        plan.backward_dx(x, w)
-        if world > 1:
-            sp._L.load().osb_set_cta_limit(0)
-        ev[3].record()
-        sp.end(y, late_labels)
-        sp.finish(work)
+    def eager_step(i, marks=None):
+        sp.finish(sp.step(xs[i % nbuf], w, ys[i % nbuf], marks=marks))
 
-    # One GPU: the five launches of a step are replayed from a CUDA graph (one graph per rotating input buffer), so
-    # the timed loop has no per-launch host work.  N > 1 stays eager: the all-reduce epoch changes every step.
+    # The launches of a step are replayed from ONE CUDA graph per rotating input buffer, so the timed loop has no
+    # per-launch host work; with N > 1 the graph holds the whole sharded step including the peer-memory all-reduce (its
+    # epoch lives in device memory).  Only the NCCL fallback stays eager.
     launch_mode = "eager"
-    run_step = step
-    if world == 1 and not args.eager:
-        graphs = [plan.capture(xs[i], w, ys[i]) for i in range(nbuf)]
-        launch_mode = "CUDA-graph replay of the 5 kernels of a step"
+    run_step = eager_step
+    if not args.eager and (world == 1 or sp.peer is not None):
+        graphs = [(plan.capture(xs[i], w, ys[i]) if world == 1 else sp.capture(xs[i], w, ys[i])) for i in range(nbuf)]
+        launch_mode = "CUDA-graph replay of the whole step" + (" incl. the peer-memory all-reduce" if world > 1 else " (5 kernels)")
 
         def run_step(i):
             graphs[i % nbuf].replay()
@@ -205,68 +270,74 @@ def run_head(args, cfg, rank, world, dev, peaks):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sp.check()
     ms = t0.elapsed_time(t1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    loss_val = float(sp.full_loss().item())
+    loss_val = float(sp.full_loss().item()) if world > 1 else float(plan.loss.item())
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    clocks = clk.summary()
+    splitk = bool(L.size("osb_head_forward_is_splitk", B, K, C))
+    fwd_name = "head_fwd_splitk_kernel" if splitk else "head_fwd_kernel"
+    gemm_flops = 2.0 * B * K * C
+    step_us = ms_per_step * 1e3
+    peak, peak_kind = pick_tensor_peak(peaks, clocks)
+    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_kind": peak_kind,
+            "step": {"flops": 3 * gemm_flops, "us": round(step_us, 2), "achieved": 3 * gemm_flops / step_us / 1e6,
+                     "frac": 3 * gemm_flops / step_us / 1e6 / peak},
+            "algorithmic_flops_per_sample": 6.0 * K * C}
+    parity = {}
+    if rank == 0:
+        parity["head"] = head_parity(cfg, xs[0], w, ys_np[0], cw, plan_kw, rows=B if B <= 2048 else 2048)
+    if world > 1:
+        parity["sharded"] = sharded_parity(cfg, sp, xs[0], w, ys[0], plan_kw, rank, world, dev)
+    if light:
+        return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=None, clocks=clocks, loss=loss_val,
+                    launches=sp.launches_per_step * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
+                    precision=parity.get("head", {}).get("precision"))
 
-    step_us_hint = ms_per_step * 1e3
-    # per-kernel times: a second, shorter loop with events between the launches (kept out of the headline loop)
-    # On one GPU the loop is queued behind ~40 ms of graph replays of the same step: the host has every launch and event
-    # queued before the first timed kernel starts (the events bracket kernels that run back to back, not the host's launch
-    # gaps), and the GPU is in the same power state as in the headline loop (behind an idle gap the first kernels run at
-    # boost clocks: 73 vs 90 us for the same forward kernel on one box).
+    # ---- per-kernel times: a second, shorter loop with CUDA events between the launches of an EAGER step, queued behind
+    # ~40 ms of replays of the same step, so that the host is ahead of the GPU (the events bracket kernels that run back
+    # to back) and the GPU is in the power state of the headline loop.  Medians over the steps.  The dominant kernel's
+    # RAW bracket is what `roofline.achieved` is computed from; no rescaling.
     n_ev = max(10, min(args.steps, 50))
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
     torch.cuda.synchronize()
-    if world == 1 and run_step is not step:
-        for i in range(max(50, int(40e3 / max(step_us_hint, 1.0)))):
-            run_step(i)
-    for i in range(n_ev):
-        step(i, evs[i])
-    torch.cuda.synchronize()
-    # median over the steps: a launch the host issued late shows up as a gap inside one bracket, not in the median
+    if world > 1:
+        dist.barrier()
+    with ClockSampler(dev.index) as clk_k:
+        if run_step is not eager_step:
+            for i in range(max(50, int(40e3 / max(step_us, 1.0)))):
+                run_step(i)
+        for i in range(n_ev):
+            eager_step(i, evs[i])
+        torch.cuda.synchronize()
+    sp.check()
     k_fwd = statistics.median(e[0].elapsed_time(e[1]) for e in evs) * 1e3
     k_dw = statistics.median(e[1].elapsed_time(e[2]) for e in evs) * 1e3
     k_dx = statistics.median(e[2].elapsed_time(e[3]) for e in evs) * 1e3
-
-    gemm_flops = 2.0 * B * K * C
-    # batches of up to ~15 row tiles of a head of <= 256 classes take the split-K forward (cluster of 8 CTAs per tile)
-    splitk = C <= 256 and K >= 512 and (B + 127) // 128 <= sp._L.load().osb_debug_head_splitk_max_clusters()
-    kernels = {"head_fwd_splitk_kernel" if splitk else "head_fwd_kernel": k_fwd,
-               "head_dw2_kernel+dw_reduce_kernel": k_dw, "head_dx2_kernel": k_dx}
+    dw_name = "head_dw2_kernel" + ("+dw_reduce_kernel" if (world == 1 or sp.peer is None) else " (partials; the reduce is the all-reduce)")
+    kernels = {fwd_name: k_fwd, dw_name: k_dw, "head_dx2_kernel": k_dx}
     dom = max(kernels, key=kernels.get)
-    step_us = ms_per_step * 1e3
-    # Duration of a kernel INSIDE the timed region: the eager brackets carry an event record on either side and none of
-    # the prologue overlap of the graph-replayed step (their sum is 3-10 % above the step), so each kernel is given its
-    # share of the measured step time.  The raw brackets stay in `kernels_us_eager`.
+    clocks_k = clk_k.summary()
+    peak_k, peak_kind_k = pick_tensor_peak(peaks, clocks_k)
     bracket_sum = sum(kernels.values())
-    eager = dict(kernels)
-    if world == 1 and run_step is not step and bracket_sum > step_us:
-        kernels = {k: v * step_us / bracket_sum for k, v in kernels.items()}
-        duration_note = ("kernels_us = share of the CUDA-event-timed step (graph replay) each kernel takes; shares from an eager "
-                         "loop with events between the launches (kernels_us_eager, medians)")
-    else:
-        duration_note = "kernels_us = medians of CUDA-event brackets around the launches of an eager loop"
-    roof = {
-        "bound": "tensor", "kernel": dom, "unit": "TFLOP/s",
-        "achieved": gemm_flops / kernels[dom] / 1e6, "peak": peaks["tc_sustained"],
-        "peak_kind": f"{peaks['src']} cuBLAS bf16 sustained (kernels timed inside a long step); burst is {peaks['tc_burst']}",
+    roof.update({
+        "kernel": dom, "achieved": gemm_flops / kernels[dom] / 1e6, "peak": peak_k, "peak_kind": peak_kind_k,
         "traffic": (load_traffic().get(dom, {}).get("bytes") if (B, K, C) == (16384, 2048, 1000) else None),
         "traffic_note": "dram read+write bytes of one launch from the committed ncu --set full capture (profiles/traffic.json)",
         "kernels_us": {k: round(v, 2) for k, v in kernels.items()},
-        "kernels_us_eager": {k: round(v, 2) for k, v in eager.items()},
-        "duration_note": duration_note,
         "kernels_tflops": {k: round(gemm_flops / v / 1e6, 1) for k, v in kernels.items()},
-        "step": {"flops": 3 * gemm_flops, "us": round(step_us, 2), "achieved": 3 * gemm_flops / step_us / 1e6,
-                 "frac": 3 * gemm_flops / step_us / 1e6 / peaks["tc_sustained"]},
-        "algorithmic_flops_per_sample": 6.0 * K * C,
-    }
+        "duration_note": "kernels_us = medians of raw CUDA-event brackets around the launches of an eager step queued behind graph "
+                         "replays of the same step; achieved = 2*B*K*C / the dominant kernel's bracket",
+        "kernels_us_share_of_step": {k: round(v * step_us / bracket_sum, 2) for k, v in kernels.items()},
+        "clocks_kernel_loop": clocks_k,
+    })
     roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["step"]["peak"], roof["step"]["peak_kind"] = peak, peak_kind
 
     # ---- end to end from pinned host buffers through the C ABI: every step copies ITS features and labels host ->
     # device and reads its loss back.  Two device input slots: the copy of step i+1 (copy stream) overlaps the kernels
@@ -283,6 +354,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
         ready = [torch.cuda.Event() for _ in range(2)]       # slot filled
         freed = [torch.cuda.Event() for _ in range(2)]       # slot consumed
         n_e2e = max(3, min(args.steps, 40))
+        loss_src = sp.peer.extra_sum[sp.peer.n_extra - 1:] if (world > 1 and sp.peer is not None) else plan.loss
 
         def prefetch(i):
             sl = i % 2
@@ -303,7 +375,7 @@ def run_head(args, cfg, rank, world, dev, peaks):
                 main.wait_event(ready[sl])
                 sp.finish(sp.step(xd[sl], w, yd[sl]))
                 freed[sl].record(main)
-                lossh.copy_(plan.loss, non_blocking=True)
+                lossh.copy_(loss_src, non_blocking=True)
 
         e2e_loop(3)
         torch.cuda.synchronize()
@@ -324,8 +396,9 @@ def run_head(args, cfg, rank, world, dev, peaks):
                "ms_per_step": ems / n_e2e,
                "note": "features+labels copied from pinned host memory every step (prefetched one step ahead on a copy stream), "
                        "loss read back every step; dX and dW stay on the device for the backbone / optimiser"}
-    return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clk.summary(), loss=loss_val,
-                launches=sp.launches_per_step * args.steps, allreduce=allreduce, launch_mode=launch_mode)
+    return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clocks, loss=loss_val,
+                launches=sp.launches_per_step * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
+                precision=parity.get("head", {}).get("precision"))
 
 
 def run_oscr(args, rank, world, dev, peaks):
@@ -431,23 +504,27 @@ def run_oscr(args, rank, world, dev, peaks):
         o_ccr, o_fpr = O.calculate_oscr(gt_np, s_np, -1)
         cpu_ms = (time.perf_counter() - t0) * 1e3
         n_q = 8000
-        from oracle import ref_port
+        from oracle import ref_loader, ref_port
+        quad = ref_loader.load("util").calculate_oscr if ref_loader.available() else ref_port.oscr_port_quadratic
         t0 = time.perf_counter()
-        ref_port.oscr_port_quadratic(gt_np[:n_q], s_np[:n_q], -1)
+        with np.errstate(all="ignore"):
+            quad(gt_np[:n_q], s_np[:n_q], -1)
         q_ms = (time.perf_counter() - t0) * 1e3
         out["cpu_baseline"] = {"value": cpu_ms, "unit": "ms", "cores": 1, "kind": "port",
                                "sample": f"O(N log N) numpy restatement (oracle.calculate_oscr, bit-equal to the reference) on the full N={N}; "
                                          f"numpy sort is single-threaded",
                                "reference_quadratic": {"n": n_q, "ms": q_ms, "extrapolated_ms_at_1M": q_ms * (N / n_q) ** 2,
-                                                       "note": "reference's own O(U*N) loop (util.py:113-118) timed at n rows; 1M figure is an N^2 extrapolation"}}
+                                                       "kind": "reference" if ref_loader.available() else "port",
+                                                       "note": "the reference's own util.calculate_oscr (O(U*N) loop, util.py:113-118) timed at n rows; 1M figure is an N^2 extrapolation"}}
         out["parity"] = {"bit_exact_vs_oracle": bool(np.array_equal(ccr, o_ccr) and np.array_equal(fpr, o_fpr, equal_nan=True))}
     return out
 
 
 def run_resnet(args, rank, world, dev):
     """BASELINE.json cfg 2: ResNet-50 (torchvision / cuDNN, bf16 autocast, channels_last) + fused entropic head,
-    Protocol-1 shape (116 classes), B = 256 synthetic 224x224 images per GPU; whole training step and the head's share."""
-    import openset_imagenet_b200 as osb
+    Protocol-1 shape (116 classes), B = 256 synthetic 224x224 images per GPU; whole training step and the head's share.
+    The model is the reference's (fc 2048 -> 116 with bias, logits 116 -> 116 without, train.py:350-352); the two
+    stacked linears run COLLAPSED as one 2048 -> 116 fused tcgen05 head (model.ResNet50, fused='collapsed')."""
     from openset_imagenet_b200 import synth
     from openset_imagenet_b200.model import ResNet50
     B, C = 256, 116
@@ -476,14 +553,19 @@ def run_resnet(args, rank, world, dev):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
-    # the head alone on the same shapes (features [B, 116] bf16 -> 116 classes), forward + backward
-    feats = torch.randn(B, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    # the head alone on the same shapes (pooled features [B, 2048] bf16 -> 116 classes, collapsed weights), forward + backward
+    feats = torch.randn(B, 2048, device=dev, dtype=torch.bfloat16, requires_grad=True)
+
+    def head_only():
+        w_eff, b_eff = model.collapsed_weights()
+        model.logits.loss(feats, ys[0], weight=w_eff, bias=b_eff).backward()
+
     for _ in range(3):
-        model.logits.loss(feats, ys[0]).backward()
+        head_only()
     torch.cuda.synchronize()
     a.record()
     for _ in range(20):
-        model.logits.loss(feats, ys[0]).backward()
+        head_only()
     b.record()
     torch.cuda.synchronize()
     head_us = a.elapsed_time(b) / 20 * 1e3
@@ -491,26 +573,69 @@ def run_resnet(args, rank, world, dev):
             "ms_per_step": ms, "steps": steps, "warmup": warm, "head_fwd_bwd_us": head_us, "head_share": head_us * 1e-3 / ms,
             "loss": float(j.item()),
             "config": {"workload": "ResNet-50 + fused entropic head, Protocol 1 shape (116 classes), B=256 synthetic 224x224 images, "
-                                   "bf16 autocast, channels_last, SGD momentum", "global_batch": B * world}}
+                                   "bf16 autocast, channels_last, SGD momentum", "global_batch": B * world,
+                       "head": "fc (2048->116, bias) and logits (116->116) collapsed into one 2048->116 tcgen05 head per step; "
+                               "autograd through torch.autograd.Function (eager launches)"}}
 
 
-def head_cpu_baseline(cfg, sample_rows, iters):
-    """The reference path op for op on the host cores (oracle/ref_port.py), on `sample_rows` rows of the workload."""
+def reference_head_step(cfg, rows):
+    """The reference's own code for one step of the path on the host cores: nn.Linear -> losses.EntropicOpensetLoss (or the
+    CrossEntropyLoss configurations of train.py:343,347) -> .item() -> backward (train.py:132-139), then the validation
+    side of the same batch: softmax + metrics.confidence (train.py:177,187-192).  losses.py / metrics.py are the
+    reference's files, loaded unmodified (oracle/ref_loader.py) from /root/reference or from the verbatim copies under
+    oracle/_ref; only when neither exists does the op-for-op port (oracle/ref_port.py) stand in."""
     from openset_imagenet_b200 import synth as O
-    from oracle import ref_port
+    from oracle import ref_loader
     torch.manual_seed(0)
     K, C = cfg["K"], cfg["C"]
     lin = torch.nn.Linear(K, C, bias=False)
-    loss_fn = ref_port.EntropicLossPort(C, 1.0)
-    x = torch.randn(sample_rows, K, requires_grad=True)
-    y = torch.tensor(O.make_labels(sample_rows, C, cfg["neg_frac"], seed=7))
-    ref_port.head_step_port(lin, loss_fn, x, y, 1.0 / C)
+    x = torch.randn(rows, K, requires_grad=True)
+    if ref_loader.available():
+        losses, metrics = ref_loader.load("losses"), ref_loader.load("metrics")
+        kind, conf_fn = "reference", metrics.confidence
+        src = f"the reference's losses.py + metrics.py ({ref_loader.source()})"
+    else:
+        from oracle import ref_port
+        losses = None
+        kind, conf_fn = "port", ref_port.confidence_port
+        src = "oracle/ref_port.py (reference files not available)"
+    if cfg["variant"] == "garbage":
+        y_np = O.make_labels(rows, C - 1, cfg["neg_frac"], seed=7, neg_label=C - 1)
+        cw = torch.tensor(O.class_weights_from_labels(np.concatenate([y_np, np.arange(C)]), C))
+        loss_fn = torch.nn.CrossEntropyLoss(weight=cw)                       # train.py:346-347
+        offset, unknown_class, last_valid = 0.0, C - 1, -1                   # train.py:156-159
+    else:
+        y_np = O.make_labels(rows, C, cfg["neg_frac"], seed=7)
+        loss_fn = losses.EntropicOpensetLoss(C, 1.0) if losses is not None else ref_port.EntropicLossPort(C, 1.0)
+        offset, unknown_class, last_valid = 1.0 / C, -1, None                # train.py:160-163
+    y = torch.tensor(y_np)
+
+    def step():
+        lin.zero_grad(set_to_none=True)
+        x.grad = None
+        logits = lin(x)
+        j = loss_fn(logits, y)
+        val = j.item()
+        j.backward()
+        with torch.no_grad():
+            scores = torch.nn.functional.softmax(logits, dim=1)
+            conf = conf_fn(scores, y, offset=offset, unknown_class=unknown_class, last_valid_class=last_valid)
+        return val, conf
+
+    return step, kind, src
+
+
+def time_reference(cfg, rows, steps, warmup):
+    step, kind, src = reference_head_step(cfg, rows)
+    for _ in range(warmup):
+        step()
     ts = []
-    for _ in range(iters):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        ref_port.head_step_port(lin, loss_fn, x, y, 1.0 / C)
+        step()
         ts.append(time.perf_counter() - t0)
-    return sample_rows / statistics.median(ts), ts
+    total = sum(ts)
+    return rows * len(ts) / total, total / len(ts) * 1e3, kind, src
 
 
 _REAL_STDOUT = None
@@ -524,6 +649,11 @@ def emit(line: dict):
         sys.stdout.flush()
     else:
         os.write(_REAL_STDOUT, data)
+
+
+def workload_name(cfg):
+    return (f"{cfg['variant']} open-set head fwd+bwd, {cfg['K']}->{cfg['C']} classes, {cfg['B']} bf16 feature rows per GPU, "
+            f"{cfg['neg_frac']:.2f} negatives (BASELINE.json {'large-head stress config' if cfg is HEAD else 'BG config'})")
 
 
 def main():
@@ -540,35 +670,41 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="head", choices=["head", "bg", "oscr", "resnet"])
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--eager", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph (N=1)")
+    ap.add_argument("--eager", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-oscr", action="store_true")
-    ap.add_argument("--sm-reserve", type=int, default=32, help="SMs left to the gradient all-reduce while dX runs (N > 1)")
+    ap.add_argument("--no-sub", action="store_true", help="skip the bg / resnet sub-objects of the default line")
+    ap.add_argument("--sm-reserve", type=int, default=16, help="SMs left to the gradient all-reduce while dX runs (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()
     cfg = HEAD if args.workload != "bg" else BG
-    workload_name = (f"{cfg['variant']} open-set head fwd+bwd, {cfg['K']}->{cfg['C']} classes, {cfg['B']} bf16 feature rows per GPU, "
-                     f"{cfg['neg_frac']:.2f} negatives (BASELINE.json {'large-head stress config' if cfg is HEAD else 'BG config'})")
     peaks = load_peaks()
 
     if args.impl == "reference":
         if rank != 0:
             return
         torch.set_num_threads(os.cpu_count() or 1)
-        # bounded sample: size the per-step sample so steps+warmup stay within ~2 minutes
-        v0, ts = head_cpu_baseline(cfg, 256, 1)
-        per_row = ts[0] / 256
-        rows = int(min(cfg["B"], max(64, 90.0 / max(per_row * (args.steps + args.warmup), 1e-9))))
-        rows = 1 << (rows.bit_length() - 1)
-        rows = max(64, min(rows, 4096))
-        value, ts = head_cpu_baseline(cfg, rows, max(1, min(args.steps, 200)))
-        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": len(ts), "warmup": 1,
-                "ms_per_step": statistics.median(ts) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        # the same configuration as our arm: the whole job's rows per step (gpus x rows per GPU), the same step and
+        # warm-up counts, bounded only if a probe says the run would exceed ~4 minutes
+        rows = cfg["B"] * max(args.gpus, 1)
+        steps, warmup = args.steps, args.warmup
+        _, probe_ms, _, _ = time_reference(cfg, min(rows, 4096), 1, 1)
+        est_s = probe_ms * 1e-3 * rows / min(rows, 4096) * (steps + warmup)
+        bounded = None
+        if est_s > 240.0:
+            steps = max(3, int(steps * 240.0 / est_s))
+            warmup = min(warmup, 3)
+            bounded = f"steps bounded to {steps} (+{warmup} warm-up): {args.steps} steps were estimated at {est_s:.0f} s"
+        value, ms_step, kind, src = time_reference(cfg, rows, steps, warmup)
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": workload_name, "sample_rows_per_step": rows},
-                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"{rows} rows per step of the same workload, float32, torch CPU ({torch.get_num_threads()} threads): "
-                                           "nn.Linear -> EntropicOpensetLoss port -> backward -> softmax -> confidence port (oracle/ref_port.py)"},
+                "config": {"workload": workload_name(cfg), "global_batch": rows, "in_features": cfg["K"], "classes": cfg["C"],
+                           "parallelism": f"host CPU, {torch.get_num_threads()} threads"},
+                "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+                                 "sample": f"{rows} rows per step x {steps} steps of the same workload, float32, torch CPU "
+                                           f"({torch.get_num_threads()} threads): nn.Linear -> loss -> .item() -> backward -> softmax -> "
+                                           f"confidence with {src}" + (f"; {bounded}" if bounded else "")},
                 "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -585,6 +721,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import openset_imagenet_b200  # noqa: F401  (loads libosb.so; raises if missing)
 
+    def sub_head(cfg_):
+        r_ = run_head(args, cfg_, rank, world, dev, peaks, light=True)
+        return {"metric": METRIC.replace("EOS", "BG" if cfg_ is BG else "EOS"), "value": r_["value"], "unit": "samples/s",
+                "ms_per_step": r_["ms_per_step"], "us_per_step": r_["ms_per_step"] * 1e3, "steps": args.steps, "warmup": args.warmup,
+                "config": {"workload": workload_name(cfg_), "global_batch": cfg_["B"] * world, "launch": r_["launch_mode"],
+                           "precision": r_["precision"]},
+                "gpu_launches": r_["launches"], "loss": r_["loss"], "parity": r_["parity"], "clocks": r_["clocks"]}
+
     if args.workload == "resnet":
         o = run_resnet(args, rank, world, dev)
         if rank == 0:
@@ -599,25 +743,33 @@ def main():
     else:
         r = run_head(args, cfg, rank, world, dev, peaks)
         oscr = None if args.no_oscr else run_oscr(args, rank, world, dev, peaks)
+        bg = sub_head(BG) if (cfg is HEAD and not args.no_sub) else None
+        resnet = run_resnet(args, rank, world, dev) if (cfg is HEAD and not args.no_sub and world == 1) else None
         if rank == 0:
             line = {"metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                    "config": {"workload": workload_name, "global_batch": cfg["B"] * world, "in_features": cfg["K"],
+                    "config": {"workload": workload_name(cfg), "global_batch": cfg["B"] * world, "in_features": cfg["K"],
                                "classes": cfg["C"], "parallelism": f"batch-sharded x{world}; {r['allreduce']}" if world > 1 else "single GPU",
+                               "precision": r["precision"],
                                "l2": "3 rotating 64 MB feature buffers + 64 MB dX + 32 MB dZ per step: working set > 126 MB L2",
                                "launch": r["launch_mode"]},
                     "roofline": r["roofline"], "e2e": r["e2e"], "clocks": r["clocks"], "gpu_launches": r["launches"],
-                    "loss": r["loss"], "peaks": peaks}
+                    "loss": r["loss"], "parity": r["parity"], "peaks": peaks}
             if world == 1 and not args.no_e2e:
                 torch.set_num_threads(os.cpu_count() or 1)
-                rows = 2048
-                v, ts = head_cpu_baseline(cfg, rows, 5)
-                line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                                        "sample": f"{rows} rows of the same workload x 5 steps, float32 torch CPU: nn.Linear -> EntropicOpensetLoss "
-                                                  "port -> backward -> softmax -> confidence port (oracle/ref_port.py)"}
+                v, ms_step, kind, src = time_reference(cfg, cfg["B"], 5, 2)
+                line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+                                        "sample": f"{cfg['B']} rows per step x 5 steps (2 warm-up) of the same workload, float32 torch CPU: "
+                                                  f"nn.Linear -> loss -> .item() -> backward -> softmax -> confidence with {src}"}
             if oscr is not None:
                 line["oscr"] = oscr
+                if "parity" in oscr:
+                    line["parity"]["oscr"] = oscr["parity"]
+            if bg is not None:
+                line["bg"] = bg
+            if resnet is not None:
+                line["resnet"] = resnet
             emit(line)
     if world > 1:
         import torch.distributed as dist

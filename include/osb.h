@@ -2,7 +2,8 @@
  * osb.h — C ABI of the B200-native open-set head + evaluation path ("osb" = open-set B200).
  *
  * One shared library (openset_imagenet_b200/csrc/libosb.so, sm_100a only) exports exactly the
- * functions declared here.  Plain pointers and sizes only; no C++/torch types.  The reference
+ * functions declared here, plus the developer hooks of osb_debug.h (timing probes, A/B switches; nothing in the
+ * product path or in bench.py calls those).  Plain pointers and sizes only; no C++/torch types.  The reference
  * (AIML-IfI/openset-imagenet) is pure Python and has no FFI of its own, so each entry cites the
  * reference call site (file:line, relative to the reference root) whose arithmetic it replaces;
  * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
@@ -10,7 +11,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its comment says host;
  *   - the caller owns all memory, including workspaces (size from the matching *_workspace_bytes);
- *     the library never allocates or frees device memory and keeps no per-call state;  a workspace
+ *     the library never allocates or frees device memory and keeps no mutable state between calls
+ *     (per-thread caches of encoded TMA descriptors and a cached device query are the only statics);  a workspace
  *     must be zero-filled ONCE by its owner before first use, every entry leaves it reusable, and one
  *     workspace must not be shared by calls that may run concurrently on different streams;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OSB_ABI_VERSION 2
+#define OSB_ABI_VERSION 3
 
 /* status codes */
 #define OSB_OK             0
@@ -45,9 +47,12 @@ extern "C" {
 #define OSB_SOFTMAX  1
 #define OSB_GARBAGE  2
 
-/* element types of logits / dlogits */
+/* element types of logits / dlogits (osb_loss_from_logits) and of dx (osb_head_backward) */
 #define OSB_F32  0
 #define OSB_BF16 1
+
+/* osb_head_forward flags */
+#define OSB_FWD_DEN_FROM_PREV_KERNEL 1   /* see osb_head_forward */
 
 /* label types accepted by the OSCR row reduce (`gt` is float32 in the reference's npz files,
  * train.py:212, and cast with astype(int) at util.py:100) */
@@ -60,10 +65,6 @@ int         osb_abi_version(void);
 const char* osb_last_error(void);            /* host string, valid until the next failing call on this thread */
 int         osb_device_check(void);          /* OSB_OK iff the current device is compute capability 10.x */
 int         osb_sm_count(void);              /* SM count of the current device (148 on B200), <0 on error */
-/* Upper bound on the grid of the persistent head kernels (forward, dX) and of osb_label_stats; 0 = one CTA per SM
- * (default).  Set it to SMs - k while a collective runs beside them so that the collective's CTAs find free SMs, or to a
- * handful while the label statistics run beside a GEMM.  Returns the old value. */
-int         osb_set_cta_limit(int max_ctas);
 
 /* ---- labels -> denominator and counts ------------------------------------------------------ *
  * Replaces the host-synchronising label bookkeeping of losses.py:18-26 and the implicit reductions
@@ -74,10 +75,12 @@ int         osb_set_cta_limit(int max_ctas);
  *                        ignored rows, rows whose label is out of range}.
  * Out-of-range labels (reference: IndexError / device assert) never fault: they are counted in
  * counts[3], treated as ignored rows, and poison the loss with NaN in the consumers below.
+ * max_ctas > 0 bounds the grid (a caller that runs the statistics beside a GEMM keeps them on a few SMs; the result
+ * does not depend on the grid), 0 = default.
  */
 int osb_label_stats(const int64_t* y, const float* class_w, int64_t B, int C, int variant,
                     int64_t ignore_index, double* den, int64_t* counts,
-                    void* ws, size_t ws_bytes, void* stream);   /* ws: osb_loss_workspace_bytes(B) */
+                    void* ws, size_t ws_bytes, int max_ctas, void* stream);   /* ws: osb_loss_workspace_bytes(B) */
 
 /* ---- loss from materialised logits --------------------------------------------------------- *
  * Drop-in arithmetic of EntropicOpensetLoss.__call__ (losses.py:16-29) and of the two
@@ -105,55 +108,81 @@ int osb_loss_from_logits(const void* logits, int dtype, int64_t ld, const int64_
                          void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused head: linear -> softmax statistics -> loss -> grad-logits -> dX, dW, db ---------- *
- * Replaces model.py:23-26,37-38 (the logits linear), losses.py:16-29 / train.py:343,347 (loss),
+ * Replaces model.py:20-26,37-38 (resnet_base.fc and the logits linear), losses.py:16-29 / train.py:343,347 (loss),
  * train.py:177 (softmax for confidence/OSCR, reduced to per-row statistics) and the autograd
  * backward of all of them (train.py:138).  tcgen05/TMEM GEMMs fed by TMA; the logits live only in
  * TMEM/registers.
  *   x [B, K] bf16 row-major (ldx elements), w [C, K] bf16 row-major (nn.Linear layout), bias [C]
  *   float32 or NULL.  K % 64 == 0, C <= 1024.
- * forward : loss_num/loss/row_* as above; dz (nullable) [B, lddz] bf16 = UN-scaled grad-logits
- *           saved for backward (lddz % 8 == 0, lddz >= C).
- * backward: dx (nullable) [B, lddx] bf16 = g * dz @ w ; dw [C, K] float32 = g * dz^T @ x ;
- *           db (nullable) [C] float32 = g * column sums of dz ; g = gscale[0] (device) or 1.
+ * forward : loss_num[0] (double) = sum of the un-normalised row losses; loss[0] (float) = loss_num / den[0], or
+ *           (float)loss_num when den is NULL (a batch-sharded caller divides by the global denominator itself);
+ *           row_* as in osb_loss_from_logits.
+ *           dz (nullable) [dz_planes][B, lddz] bf16 = DENOMINATOR-FREE grad-logits  omega_i (p_i - t_i)
+ *           (lddz % 8 == 0, lddz >= C, planes B*lddz elements apart): the forward kernel does not depend on the label
+ *           statistics, and backward divides by den.  dz_planes = 1: one bf16 rounding of dZ (2^-9 per element,
+ *           ~1e-3 norm-wise in dW / dX).  dz_planes = 2 ("exact"): plane 1 holds the bf16 rounding RESIDUAL of plane 0,
+ *           and the backward GEMMs accumulate both planes in fp32 (2^-17 per element) at twice the MMA count -
+ *           free for the launch-latency-bound protocol heads (C <= 256).
+ *           flags & OSB_FWD_DEN_FROM_PREV_KERNEL: the caller promises that the kernel directly in front of this
+ *           call on `stream` is the one that writes den (osb_label_stats, or osb_peer_sum after it) and that ITS
+ *           predecessor has completed the inputs: small batches are then launched with programmatic stream
+ *           serialization, run under that kernel, and wait for it only before den is read.
+ *           max_ctas > 0 bounds the persistent grids (forward, dX) so that a collective running beside them finds
+ *           free SMs; 0 = one CTA per SM.
+ * backward: g = gscale[0] (device, NULL = 1) / den[0];  dx (nullable) [B, lddx] of dx_dtype (OSB_BF16 or OSB_F32)
+ *           = g * dz @ w ; dw [C, K] float32 = g * dz^T @ x ; db (nullable) [C] float32 = g * column sums of dz.
  */
 size_t osb_head_workspace_bytes(int64_t B, int K, int C);
 int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
                      const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
-                     int64_t ignore_index, const double* den, int valid_cols,
+                     int64_t ignore_index, const double* den /* nullable */, int valid_cols,
                      double* loss_num, float* loss,
                      float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
-                     void* dz, int64_t lddz, void* ws, size_t ws_bytes, void* stream);
-/* osb_head_forward_after_labels(1): the caller promises that, on the stream of its next osb_head_forward calls, the
- * kernel directly in front of the forward is osb_label_stats (train.py:135: the loss follows the logits of the same batch,
- * so the features are complete before the label statistics start).  Small batches (the split-K forward) are then launched
- * with programmatic stream serialization: operands are loaded and multiplied while the statistics still run, and the kernel
- * waits for them before it reads `den`.  Thread-local; returns the previous setting; 0 restores plain stream order. */
-int osb_head_forward_after_labels(int on);
-int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
-                      int64_t B, int K, int C, const float* gscale,
-                      void* dx, int64_t lddx, float* dw, float* db,
+                     void* dz, int64_t lddz, int dz_planes, int flags, int max_ctas,
+                     void* ws, size_t ws_bytes, void* stream);
+int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, const double* den, const void* x, int64_t ldx,
+                      const void* w, int64_t B, int K, int C, const float* gscale,
+                      void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas,
                       void* ws, size_t ws_bytes, void* stream);
+/* 1 when osb_head_forward runs this shape as the split-K cluster kernel (small batches, C <= 256), else 0 */
+int osb_head_forward_is_splitk(int64_t B, int K, int C);
 
 /* ---- multi-GPU: all-reduce of dW over NVLink peer memory, fused with the split-K reduction ----- *
  * The reference has no collective at all (script/train_all.py:96-118 runs independent jobs); this is what a
  * batch-sharded head needs instead of `reduce locally, then NCCL`.
- * osb_head_backward_dw_partials runs only the dW GEMM: `osb_head_dw_splits(B,K,C)` fp32 partial matrices [C,K] are
- * left at byte offset osb_head_dw_partials_offset() of the workspace, consecutive splits C*K elements apart.
- * osb_head_dw_allreduce (one launch per rank, every rank must call it with the same epoch): rank r sums slice r of
- * ALL ranks' partials in a fixed order (bit-identical result on every rank), scales by gscale[0] and stores it
- * into every rank's dW; `n_extra` floats per rank (db, loss) are summed into extra_out.  The four pointer tables
- * are HOST arrays of `world` DEVICE pointers to peer-mapped memory (torch.distributed._symmetric_memory):
- * partial buffers, dW buffers, extra vectors, flag areas of osb_head_dw_allreduce_flag_bytes(world) bytes (zeroed
- * once).  epoch: non-zero, +1 per call.  A rank that waits ~2 s for a peer gives up and writes the epoch to
- * flag word [2*world] instead of hanging.  max_ctas bounds the grid (default 32) so the kernel overlaps dX. */
+ * osb_head_backward_dw_partials runs only the dW GEMM: `osb_head_dw_splits(B,K,C)` fp32 partial matrices [C,K]
+ * (UN-scaled: sums of dz * x) are left at byte offset osb_head_dw_partials_offset() of the workspace, consecutive
+ * splits C*K elements apart; db_partial (nullable) [C] float32 receives the un-scaled column sums of dz.
+ * osb_head_dw_allreduce (one launch per rank): rank r sums slice r of ALL ranks' partials in a fixed order
+ * (bit-identical result on every rank), scales by gscale[0] / den[0] and stores it into every rank's dW; `n_extra`
+ * floats per rank are summed into extra_out: the first n_extra - n_plain of them (db) are scaled like dW, the last
+ * n_plain (loss numerators, counts) are plain sums.  den is the GLOBAL denominator (device double; constant for the
+ * entropic loss, osb_peer_sum output otherwise).  The four pointer tables are HOST arrays of `world` DEVICE pointers
+ * to peer-mapped memory (torch.distributed._symmetric_memory): partial buffers, dW buffers, extra vectors, flag areas
+ * of osb_head_dw_allreduce_flag_bytes(world) bytes (zeroed once).  The epoch lives in the flag area (device memory)
+ * and advances by one per launch, so the launch is CUDA-graph capturable and every replay is a new epoch; all ranks
+ * must launch the same number of times.  A rank that waits ~2 s for a peer gives up: it stores nothing, sets every
+ * plain extra to NaN and writes the epoch to the error word (osb_head_dw_allreduce_error reads it back, host sync).
+ * max_ctas bounds the grid (default 32) so the kernel overlaps dX. */
 size_t osb_head_dw_partials_offset(void);
 int osb_head_dw_splits(int64_t B, int K, int C);
-int osb_head_backward_dw_partials(const void* dz, int64_t lddz, const void* x, int64_t ldx, int64_t B, int K, int C,
+int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
+                                  int64_t B, int K, int C, float* db_partial,
                                   void* ws, size_t ws_bytes, void* stream);
 size_t osb_head_dw_allreduce_flag_bytes(int world);
 int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,
                           void* const* peer_flags, int rank, int world, int splits, int64_t n, int64_t split_stride,
-                          float* extra_out, int n_extra, const float* gscale, uint32_t epoch, int max_ctas, void* stream);
+                          float* extra_out, int n_extra, int n_plain, const float* gscale, const double* den,
+                          int max_ctas, void* stream);
+int osb_head_dw_allreduce_error(const void* flags_local, int world, uint32_t* epoch_out);   /* host sync; 0 = no failure */
+
+/* Sum of up to 8 doubles over the ranks through peer memory (the loss denominator of the softmax / garbage variants,
+ * train.py:343,347, for a batch-sharded step): every rank stores its values as (32 bits, epoch) words into every
+ * peer's slot area and sums what arrives in rank order (bit-identical everywhere).  One CTA, ~5 us, graph capturable
+ * (the epoch lives in the slot area: osb_peer_sum_bytes(world) bytes per rank, peer-mapped, zeroed once).
+ * peer_slots: HOST array of `world` DEVICE pointers.  Times out like the all-reduce (out = NaN). */
+size_t osb_peer_sum_bytes(int world);
+int osb_peer_sum(const double* in, double* out, int n, void* const* peer_slots, int rank, int world, void* stream);
 
 /* ---- confidence (metrics.py:8-42) ---------------------------------------------------------- *
  *   scores [N, ld] float32, y [N] int64.

@@ -2,6 +2,9 @@
 
 ``python -m openset_imagenet_b200._build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
 without a GPU; the resulting .so is git-ignored but travels to the GPU box with the snapshot.
+Every source is compiled to an object on its own (in parallel) and the objects are linked into one
+shared library; a missing source is an error.  Build log and source fingerprint are written next to
+the library (``libosb.build.log``, ``libosb.stamp``; both git-ignored).
 """
 from __future__ import annotations
 
@@ -10,15 +13,18 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libosb.so")
-STAMP = os.path.join(CSRC, ".libosb.stamp")
+STAMP = os.path.join(CSRC, "libosb.stamp")
+LOG = os.path.join(CSRC, "libosb.build.log")
+OBJ_DIR = os.path.join(CSRC, "_obj")
 SOURCES = ["lib.cu", "loss_rows.cu", "confidence.cu", "oscr.cu", "hist.cu", "head_tc.cu", "dw_allreduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-Xptxas", "-v",
 ]
 
@@ -33,6 +39,7 @@ def _nvcc() -> str:
 def _fingerprint() -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(SOURCES).encode())
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
             if name.endswith((".cu", ".cuh", ".h")):
@@ -46,21 +53,44 @@ def build(force: bool = False, verbose: bool = False) -> str:
     fp = _fingerprint()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp:
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *srcs]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(CSRC, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libosb.so")
+    missing = [s for s in SOURCES if not os.path.exists(os.path.join(CSRC, s))]
+    if missing:
+        raise RuntimeError(f"libosb.so: source file(s) missing from {CSRC}: {', '.join(missing)}")
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_one(src: str):
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, cmd, proc
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = []
+    failed = []
+    for src, obj, cmd, proc in results:
+        log.append(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            failed.append(src)
+    if not failed:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *[r[1] for r in results]]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            failed.append("link")
+    text = "\n".join(log)
+    with open(LOG, "w") as f:
+        f.write(text)
+    if failed:
+        sys.stderr.write(text)
+        raise RuntimeError(f"nvcc failed building libosb.so ({', '.join(failed)})")
     if verbose:
-        print(log)
+        print(text)
     with open(STAMP, "w") as f:
         f.write(fp)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

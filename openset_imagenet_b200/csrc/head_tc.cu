@@ -5,8 +5,12 @@
 //                     arg-max, and the un-scaled grad-logits dZ (bf16, TMA store).  Heads wider than the
 //                     512 TMEM columns (C <= 1024) run as a 2-CTA cluster that splits the classes and
 //                     exchanges the per-row softmax statistics through distributed shared memory.
-//   head_dx_kernel  : dX = g * dZ W          (persistent, double-buffered TMEM accumulators)
-//   head_dw_kernel  : dW = g * dZ^T X        (split over the batch, deterministic partial reduce)
+//   head_dx2_kernel : dX = g * dZ W          (persistent, double-buffered TMEM accumulators)
+//   head_dw*_kernel : dW = g * dZ^T X        (split over the batch, deterministic partial reduce)
+//
+// dZ is stored DENOMINATOR-FREE, omega_i (p_i - t_i), as one bf16 plane or as two (plane 1 = the bf16 rounding residual of
+// plane 0; the backward GEMMs then run over both planes: K-concatenation, fp32 accumulation); g = gscale / den is applied
+// in the backward epilogues, so the forward kernel never waits for the label statistics.
 //
 // All operands are 128B-swizzled TMA tiles; one tile layout serves as K-major or MN-major operand
 // (tc05.cuh).  Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
@@ -15,6 +19,7 @@
 // Reference arithmetic: model.py:23-26,37-38 (linear), losses.py:16-29 / train.py:343,347 (losses),
 // train.py:177 + metrics.py:33-40 + util.py:109-111 (the per-row statistics), autograd of those.
 #include <stdlib.h>
+#include <type_traits>
 #include "osb_common.cuh"
 #include "row_modes.cuh"
 #include "tc05.cuh"
@@ -128,6 +133,8 @@ struct FwdArgs {
     double* loss_num; float* loss;
     float* row_ptgt; float* row_pmax; float* row_pmax_all; int32_t* row_pred;
     int write_dz;
+    int dz_planes;             // 1, or 2: plane 1 receives the bf16 rounding residual of plane 0
+    int den_from_prev;         // launched programmatically behind the kernel that writes den: wait for it before den is read
     double* partials; unsigned int* ticket;
     uint2* xch_stats;          // [row block][2][CL][128][6] (value, epoch) words: per-row statistics exchanged between the units of a group
     unsigned int* xch_epoch;   // epochs used so far on this workspace; only grows, so stale words never match
@@ -205,7 +212,7 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float* f) 
 
 // 10 warps get 168 registers each: the register file is handed out in 4-warp granules, so 320 threads are budgeted as 384
 // (a 200-register build fails to launch).
-template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED>
+template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED, bool PLANES2>
 __global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_dz, const FwdArgs a) {
@@ -338,7 +345,6 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         constexpr int G = Cfg::kGroups;
         const int q = warp & 3, h = (warp - kEpiWarp0) >> 2;
         const int r_in_tile = q * 32 + lane;
-        const float inv_den = (float)(1.0 / a.den[0]);
         const float s_uniform = a.t_uniform * (float)a.C;
         const int c_base = h * G * 32;                      // this warp's columns: [c_base, c_base + G * 32) of the unit's BN
         uint8_t* my_stage = sDz + (warp - kEpiWarp0) * 2 * kStageWarpBytes;
@@ -508,45 +514,60 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 sts_ll(sx + 6, m, eps); sts_ll(sx + 7, s, eps);
             }
             if (tr) a.trace[blockIdx.x * 64 + it * 8 + 5] = gtime();
-            // ---- un-scaled grad-logits  dz = (S p - T) / den = coef * e - T/den  -> bf16 -> swizzled smem -> TMA store ----
+            // ---- denominator-free grad-logits  dz = S p - T = coef * e - T  -> bf16 -> swizzled smem -> TMA store ----
             // (a thread owns a row, so direct stores would scatter 16-byte pieces over 32 rows per instruction; the TMA
             // store writes whole 128-byte lines and clips the columns >= C and the rows >= B itself)
             if (a.write_dz) {
                 const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
-                const float coef = live ? inv_den * rm.omega / s : 0.f;
+                const float coef = live ? rm.omega / s : 0.f;
                 const float coef_e = coef * fast_exp2((m_slice - m) * kLog2e);   // e was taken relative to the slice max
-                const float t_all = (rm.mode == kRowUniform) ? inv_den * a.t_uniform : 0.f;
-                const float t_hot = (rm.mode == kRowOneHot) ? inv_den * rm.omega : 0.f;
+                const float t_all = (rm.mode == kRowUniform) ? a.t_uniform : 0.f;
+                const float t_hot = (rm.mode == kRowOneHot) ? rm.omega : 0.f;
                 const float gy = fmaf(coef, fast_exp2((zy_own - m) * kLog2e), -t_all) - t_hot;   // label column
 #pragma unroll
                 for (int b = 0; b < (G + 1) / 2; ++b) {         // boxes of 64 columns
                     const int c0 = c_base + b * 64;
                     if (c0 < ncols) {
-                        uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
-                        if (lane == 0) tma_store_wait_read<1>();        // the store that read this buffer two boxes ago is done
-                        __syncwarp();
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int g = 2 * b + hh;
-                            if (g < G && c0 + hh * 32 < ncols) {
-                                float gl[32];
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) gl[i] = fmaf(coef_e, __uint_as_float(v[g < G ? g : 0][i]), -t_all);
-#pragma unroll
-                                for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, hh * 4 + cch, gl + cch * 8);
-                            }
-                        }
-                        // the label column carries the -T term of a one-hot row: patched in the staged row by its owner
                         const int cl = y_local - c0;
-                        if (y_local >= 0 && cl >= 0 && cl < 64)
-                            *reinterpret_cast<__nv_bfloat16*>(sbuf + lane * 128 + (((cl >> 3) ^ (lane & 7)) << 4) + (cl & 7) * 2) = __float2bfloat16_rn(gy);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tm_dz, sbuf, n0 + c0, tile * TM + cr * BM + q * 32);
-                            tma_store_commit();
-                        }
-                        ++n_stores;
+                        const bool patch = y_local >= 0 && cl >= 0 && cl < 64;
+                        // plane 0, and (two planes) plane 1 = what the bf16 rounding of plane 0 dropped: straight-line code,
+                        // the second box behind a warp-uniform branch
+                        auto emit = [&](auto lo_tag) {
+                            constexpr bool LO = decltype(lo_tag)::value;
+                            uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
+                            if (lane == 0) tma_store_wait_read<1>();        // the store that read this buffer two boxes ago is done
+                            __syncwarp();
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int g = 2 * b + hh;
+                                if (g < G && c0 + hh * 32 < ncols) {
+#pragma unroll
+                                    for (int cch = 0; cch < 4; ++cch) {
+                                        float gl[8];
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) {
+                                            const float gv = fmaf(coef_e, __uint_as_float(v[g < G ? g : 0][cch * 8 + i]), -t_all);
+                                            gl[i] = LO ? gv - __bfloat162float(__float2bfloat16_rn(gv)) : gv;
+                                        }
+                                        stage_chunk(sbuf, lane, hh * 4 + cch, gl);
+                                    }
+                                }
+                            }
+                            // the label column carries the -T term of a one-hot row: patched in the staged row by its owner
+                            if (patch) {
+                                const float gp = LO ? gy - __bfloat162float(__float2bfloat16_rn(gy)) : gy;
+                                *reinterpret_cast<__nv_bfloat16*>(sbuf + lane * 128 + (((cl >> 3) ^ (lane & 7)) << 4) + (cl & 7) * 2) = __float2bfloat16_rn(gp);
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_3d(&tm_dz, sbuf, n0 + c0, tile * TM + cr * BM + q * 32, LO ? 1 : 0);
+                                tma_store_commit();
+                            }
+                            ++n_stores;
+                        };
+                        emit(std::false_type{});
+                        if (PLANES2) emit(std::true_type{});
                     }
                 }
             }
@@ -623,7 +644,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tot = warp_sum(tot);
                 if (lane == 0) {
                     a.loss_num[0] = tot;
-                    a.loss[0] = (float)(tot / a.den[0]);
+                    a.loss[0] = a.den ? (float)(tot / a.den[0]) : (float)tot;
                     *a.ticket = 0u;
                     if (CL > 1) *a.xch_epoch = ep_base + (uint32_t)((n_tiles + n_clusters - 1) / n_clusters) + 1u;
                 }
@@ -640,135 +661,11 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (a.trace && threadIdx.x == 0) a.trace[(384 + blockIdx.x / 32) * 64 + (blockIdx.x % 32) * 2 + 1] = gtime();
 }
 
-// =================================================================================================
-// dX = g * dZ W : A = dZ tile (K-major over classes), B = W tile viewed MN-major (N = feature index)
-// =================================================================================================
 constexpr int kDxBN = 256;
-constexpr int kDxStages = 4;
-constexpr int kDxStageBytes = kABytes + 4 * kBoxBytes;          // 48 KB
-constexpr int kDxOffStage = kDxStages * kDxStageBytes;
-constexpr int kDxOffBars = kDxOffStage + 4 * 2 * kStageWarpBytes;
-constexpr int kDxSmemBytes = kDxOffBars + (2 * kDxStages + 4) * 8 + 16 + 1024;
-static_assert(kDxSmemBytes <= 232448, "dx kernel shared memory");
-
-__global__ void __launch_bounds__(kThreads, 1)
-head_dx_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, const float* __restrict__ gscale) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = align1024(smem_raw);
-    uint8_t* sStage = smem + kDxOffStage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDxOffBars);
-    uint64_t* full = bars; uint64_t* empty = full + kDxStages;
-    uint64_t* t_full = empty + kDxStages; uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kDxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        fence_barrier_init();
-        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dx);
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tbase = *tmem_slot;
-    const int m_tiles = (B + BM - 1) / BM, n_tiles = (K + kDxBN - 1) / kDxBN;
-    const int total = m_tiles * n_tiles;
-    const int n_kb = (C + BK - 1) / BK;
-
-    // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
-    if (warp == 0) {
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * kDxStageBytes;
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&full[s], kDxStageBytes);
-                    tma_load_2d(st, &tm_dz, &full[s], kb * BK, mt * BM);                        // 64 classes x 128 rows
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)                                                  // 64 features x 64 classes
-                        tma_load_2d(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + j * 64, kb * BK);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = make_idesc_bf16(BM, kDxBN, false, true);
-        uint32_t it = 0, tc = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
-            const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-            mbar_wait(&t_empty[buf], tph ^ 1);
-            tc_fence_after_sync();
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const uint32_t s = it % kDxStages, ph = (it / kDxStages) & 1;
-                mbar_wait(&full[s], ph);
-                tc_fence_after_sync();
-                const uint32_t a_addr = smem_u32(smem + s * kDxStageBytes);
-                const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_mnmajor(a_addr + kABytes, kBoxBytes);
-                const int rem = C - kb * BK;
-                const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)        // +32 B (K-major) / +2048 B (MN-major) per 16 K, in 16-byte units
-                        if (k < ksteps) umma_bf16(tbase + buf * kDxBN, adesc + 2 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
-                    umma_commit(&empty[s]);
-                    if (kb == n_kb - 1) umma_commit(&t_full[buf]);
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        uint8_t* my_stage = sStage + q * 2 * kStageWarpBytes;
-        const float gs = gscale ? gscale[0] : 1.f;
-        uint32_t tc = 0, n_stores = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
-            const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-            mbar_wait(&t_full[buf], tph);
-            tc_fence_after_sync();
-            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kDxBN; c0 += 64) {
-                uint8_t* sbuf = my_stage + (n_stores & 1) * kStageWarpBytes;
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
-                    tmem_ld32(t_row + c0 + h * 32, v);
-                    tmem_ld_wait();
-                    float g[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[i]);
-#pragma unroll
-                    for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tm_dx, sbuf, nt * kDxBN + c0, mt * BM + q * 32);
-                    tma_store_commit();
-                }
-                ++n_stores;
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
-        }
-        if (lane == 0) tma_store_wait_read<0>();      // staging buffers read; the stores land before the grid ends
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tbase, 512);
-}
-
 // =================================================================================================
-// dX with CTA pairs (cta_group::2): one cluster of 2 CTAs per 256 rows x 256 features, M = 256 MMAs.
+// dX = g * dZ W with CTA pairs (cta_group::2): A = dZ tile (K-major over classes), B = W tile viewed MN-major (N = feature
+// index); one cluster of 2 CTAs per 256 rows x 256 features, M = 256 MMAs.  The K loop runs over the classes of every dZ
+// plane (plane 1 = rounding residual of plane 0, the W k-block is the same).
 // CTA r of the pair loads rows [128 r, +128) of the dZ tile and features [128 r, +128) of the W tile (32 KB per stage
 // instead of 48 KB), the leader issues the MMAs, each CTA drains its own 128 x 256 accumulator from its TMEM.
 // =================================================================================================
@@ -782,10 +679,11 @@ constexpr int kDx2OffBars = kDx2OffStage + 4 * (kDxBN / 64) * kStageWarpBytes;  
 constexpr int kDx2SmemBytes = kDx2OffBars + (2 * kDx2Stages + 4) * 8 + 16 + 1024;
 static_assert(kDx2SmemBytes <= 232448, "dx2 kernel shared memory");
 
+template <bool F32OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDx2Threads, 1)
 head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_w,
-                const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, const float* __restrict__ gscale,
-                long long* trace, int dbg) {
+                const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, int planes,
+                const float* __restrict__ gscale, const double* __restrict__ den, long long* trace, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sStage = smem + kDx2OffStage;
@@ -811,13 +709,15 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     const uint32_t tbase = *tmem_slot;
     const int m_tiles = (B + 255) / 256, n_tiles = (K + kDxBN - 1) / kDxBN;
     const int total = m_tiles * n_tiles;
-    const int n_kb = (C + BK - 1) / BK;
+    const int n_kb1 = (C + BK - 1) / BK;            // k-blocks of one plane
+    const int n_kb = n_kb1 * planes;
 
     if (warp == 0) {
         uint32_t it = 0;
         for (int tile = pair; tile < total; tile += n_pairs) {
             const int mt = tile / n_tiles, nt = tile % n_tiles;
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int pl = kb >= n_kb1 ? 1 : 0, kc = kb - pl * n_kb1;
                 const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * kDx2StageBytes;
@@ -826,10 +726,10 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                         if (rank == 0) mbar_arrive(&full[s]);
                     } else {
                         if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDx2StageBytes);     // both CTAs' bytes land on the leader's barrier
-                        tma_load_2d_2sm(st, &tm_dz, &full[s], kb * BK, mt * 256 + rank * 128);               // 64 classes x 128 rows
+                        tma_load_3d_2sm(st, &tm_dz, &full[s], kc * BK, mt * 256 + rank * 128, pl);            // 64 classes x 128 rows
 #pragma unroll
                         for (int j = 0; j < 2; ++j)                                                         // 64 features x 64 classes
-                            tma_load_2d_2sm(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kb * BK);
+                            tma_load_2d_2sm(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kc * BK);
                     }
                 }
                 __syncwarp();
@@ -851,7 +751,7 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                     if (trace && blockIdx.x == 0 && tc >= 1 && tc < 3 && lane == 0) trace[256 * 64 + (tc - 1) * 32 + kb] = clock64();
                     const uint32_t a_addr = smem_u32(smem + s * kDx2StageBytes);
                     const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_mnmajor(a_addr + kABytes, kBoxBytes);
-                    const int rem = C - kb * BK;
+                    const int rem = C - (kb >= n_kb1 ? kb - n_kb1 : kb) * BK;
                     const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
                     if (elect_one()) {
 #pragma unroll
@@ -875,7 +775,7 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         const int q = warp & 3, hh = (warp - kEpiWarp0) >> 2;
         constexpr int kBoxes = kDxBN / 64 / kDx2EW;                  // boxes (and staging buffers) per warp
         uint8_t* my_stage = sStage + (hh * 4 + q) * kBoxes * kStageWarpBytes;
-        const float gs = gscale ? gscale[0] : 1.f;
+        const float gs = (float)((gscale ? (double)gscale[0] : 1.0) / den[0]);
         uint32_t tc = 0;
         for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
             const int mt = tile / n_tiles, nt = tile % n_tiles;
@@ -898,7 +798,30 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                 tma_store_wait_read<0>();                            // last tile's stores have read the staging buffers
             }
             __syncwarp();
-            if (!(dbg & 2)) {
+            if (F32OUT) {
+                // fp32 dX: the warp's 128 columns are four boxes of 32 floats; two staging buffers, two rounds
+#pragma unroll
+                for (int rnd = 0; rnd < 2; ++rnd) {
+                    if (rnd) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
+#pragma unroll
+                    for (int b = 0; b < kBoxes; ++b) {
+                        const int g = rnd * kBoxes + b;
+                        uint8_t* sbuf = my_stage + b * kStageWarpBytes;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float4 o = make_float4(gs * __uint_as_float(v[g][4 * c]), gs * __uint_as_float(v[g][4 * c + 1]),
+                                                   gs * __uint_as_float(v[g][4 * c + 2]), gs * __uint_as_float(v[g][4 * c + 3]));
+                            *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tm_dx, sbuf, nt * kDxBN + hh * kBoxes * 64 + g * 32, mt * 256 + rank * 128 + q * 32);
+                            tma_store_commit();
+                        }
+                    }
+                }
+            } else if (!(dbg & 2)) {
 #pragma unroll
                 for (int b = 0; b < kBoxes; ++b) {
                     uint8_t* sbuf = my_stage + b * kStageWarpBytes;
@@ -941,7 +864,7 @@ constexpr int kDwSmemBytes = kDwOffBars + (2 * kDwStages + 1) * 8 + 16 + 1024;
 
 __global__ void __launch_bounds__(kThreads, 1)
 head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
-               int B, int K, int C, int splits, float* __restrict__ partials) {
+               int B, int K, int C, int planes, int splits, float* __restrict__ partials) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwOffBars);
@@ -965,7 +888,8 @@ head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     const int unit = blockIdx.x;
     const int sp = unit % splits, tile = unit / splits;
     const int mt = tile / n_tiles, nt = tile % n_tiles;
-    const int kb_total = (B + BK - 1) / BK;
+    // the reduction runs over the batch rows of every dZ plane (plane 1 = rounding residual, same X rows)
+    const int kb_rows = (B + BK - 1) / BK, kb_total = kb_rows * planes;
     const int kb0 = (int)((int64_t)kb_total * sp / splits), kb1 = (int)((int64_t)kb_total * (sp + 1) / splits);
 
     // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
@@ -975,12 +899,13 @@ head_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
             const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + s * kDwStageBytes;
+            const int pl = kb >= kb_rows ? 1 : 0, kr = kb - pl * kb_rows;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], kDwStageBytes);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tma_load_2d(st + j * kBoxBytes, &tm_dz, &full[s], mt * BM + j * 64, kb * BK);
+                for (int j = 0; j < 2; ++j) tma_load_3d(st + j * kBoxBytes, &tm_dz, &full[s], mt * BM + j * 64, kr * BK, pl);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tma_load_2d(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + j * 64, kb * BK);
+                for (int j = 0; j < 4; ++j) tma_load_2d(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + j * 64, kr * BK);
             }
             __syncwarp();
         }
@@ -1044,7 +969,7 @@ static_assert(kDw2SmemBytes <= 232448, "dw2 kernel shared memory");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ CUtensorMap tm_part, int B, int K, int C, int splits, long long* trace) {
+                const __grid_constant__ CUtensorMap tm_part, int B, int K, int C, int planes, int splits, long long* trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2OffBars);
@@ -1070,7 +995,7 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     const int unit = blockIdx.x >> 1;
     const int sp = unit % splits, tile = unit / splits;
     const int mt = tile / n_tiles, nt = tile % n_tiles;
-    const int kb_total = (B + BK - 1) / BK;
+    const int kb_rows = (B + BK - 1) / BK, kb_total = kb_rows * planes;     // batch rows of every dZ plane
     const int kb0 = (int)((int64_t)kb_total * sp / splits), kb1 = (int)((int64_t)kb_total * (sp + 1) / splits);
 
     // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
@@ -1080,12 +1005,13 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
             const uint32_t s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + s * kDw2StageBytes;
+            const int pl = kb >= kb_rows ? 1 : 0, kr = kb - pl * kb_rows;
             if (elect_one()) {
                 if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDw2StageBytes);     // both CTAs' bytes land on the leader's barrier
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(st + j * kBoxBytes, &tm_dz, &full[s], mt * 256 + rank * 128 + j * 64, kb * BK);
+                for (int j = 0; j < 2; ++j) tma_load_3d_2sm(st + j * kBoxBytes, &tm_dz, &full[s], mt * 256 + rank * 128 + j * 64, kr * BK, pl);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + rank * 128 + j * 64, kb * BK);
+                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(st + (2 + j) * kBoxBytes, &tm_x, &full[s], nt * kDwBN + rank * 128 + j * 64, kr * BK);
             }
             __syncwarp();
         }
@@ -1154,9 +1080,9 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 // dW = g * sum_s partials[s]  (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
 dw_reduce_kernel(const float4* __restrict__ partials, int splits, size_t n4, const float* __restrict__ gscale,
-                 float4* __restrict__ dw) {
+                 const double* __restrict__ den, float4* __restrict__ dw) {
     pdl_wait();                 // the partials come from the dW GEMM in front of this kernel
-    const float gs = gscale ? gscale[0] : 1.f;
+    const float gs = (float)((gscale ? (double)gscale[0] : 1.0) / den[0]);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 acc = partials[i];
         for (int s = 1; s < splits; ++s) {
@@ -1168,20 +1094,28 @@ dw_reduce_kernel(const float4* __restrict__ partials, int splits, size_t n4, con
     }
 }
 
-// db = g * column sums of dZ (bf16 [B, lddz]); one block per 64 columns, fixed summation order
+// db = g * column sums of dZ (bf16 [planes][B, lddz]); one block per 64 columns, fixed summation order.  den == NULL:
+// un-scaled sums (input of the cross-GPU all-reduce, which applies g / den itself).
 __global__ void __launch_bounds__(256)
-db_kernel(const __nv_bfloat16* __restrict__ dz, int64_t lddz, int B, int C, const float* __restrict__ gscale,
-          float* __restrict__ db) {
+db_kernel(const __nv_bfloat16* __restrict__ dz, int64_t lddz, int B, int C, int planes, const float* __restrict__ gscale,
+          const double* __restrict__ den, float* __restrict__ db) {
     __shared__ float sh[4][64];
     const int c = blockIdx.x * 64 + (threadIdx.x & 63);
     const int part = threadIdx.x >> 6;
     float acc = 0.f;
-    if (c < C)
+    if (c < C) {
         for (int r = part; r < B; r += 4) acc += __bfloat162float(dz[(int64_t)r * lddz + c]);
+        if (planes > 1) {
+            const __nv_bfloat16* lo = dz + (int64_t)B * lddz;
+            float acc2 = 0.f;
+            for (int r = part; r < B; r += 4) acc2 += __bfloat162float(lo[(int64_t)r * lddz + c]);
+            acc += acc2;
+        }
+    }
     sh[part][threadIdx.x & 63] = acc;
     __syncthreads();
     if (threadIdx.x < 64 && c < C) {
-        const float gs = gscale ? gscale[0] : 1.f;
+        const float gs = den ? (float)((gscale ? (double)gscale[0] : 1.0) / den[0]) : 1.f;
         db[c] = gs * (((sh[0][threadIdx.x] + sh[1][threadIdx.x]) + sh[2][threadIdx.x]) + sh[3][threadIdx.x]);
     }
 }
@@ -1263,25 +1197,16 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     stamp(1);
     pdl_trigger();              // the dW GEMM behind this kernel may set itself up; it waits for dZ (pdl_wait) before it loads
     // The epilogue threads have nothing to do until the MMAs complete: the label of the row a thread will own after the
-    // reduce-scatter, its class weight and the denominator (three dependent global round trips) are fetched now, under
-    // the operand loads.
+    // reduce-scatter and its class weight (two dependent global round trips) are fetched now, under the operand loads.
     const int te = (int)threadIdx.x - kEpiWarp0 * 32;
     const int row16 = te / kSkLanes, sub = te % kSkLanes;
     const int row = tile * BM + rank * kSkRows + row16;
     const bool row_ok = te >= 0 && row < a.B;
     int64_t y = -1;
     RowMode rm; rm.mode = kRowIgnored; rm.omega = 0.f;
-    float inv_den = 0.f;
-    if (te >= 0) {
-        if (row_ok) {
-            y = a.y[row];
-            rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, a.t_uniform * (float)a.C);
-        }
-        // Launched with programmatic stream serialization right behind label_stats_kernel (osb_head_forward_after_labels),
-        // this grid starts while that one still runs: the TMA and MMA warps only read the caller's inputs, and the epilogue
-        // warps wait here, before the denominator and long before anything is written (a no-op in a plain launch).
-        pdl_wait();
-        inv_den = (float)(1.0 / a.den[0]);
+    if (te >= 0 && row_ok) {
+        y = a.y[row];
+        rm = classify_row(a.variant, y, a.C, a.ignore_index, a.class_w, a.t_uniform * (float)a.C);
     }
 
     if (warp == 0) {
@@ -1407,13 +1332,15 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             }
         }
         s = group_sum<kSkLanes>(s); sumz = group_sum<kSkLanes>(sumz); zy = group_sum<kSkLanes>(zy);
-        // ---- un-scaled grad-logits  dz = (S p - T) / den = coef * e - T / den  (bf16, 8-byte stores: 4 columns) ----
+        // ---- denominator-free grad-logits  dz = S p - T = coef * e - T  (bf16, 8-byte stores: 4 columns); with two planes
+        //      the second one receives what the bf16 rounding of the first dropped ----
         if (a.write_dz && row_ok) {
             const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
-            const float coef = live ? inv_den * rm.omega / s : 0.f;
-            const float t_all = (rm.mode == kRowUniform) ? inv_den * a.t_uniform : 0.f;
-            const float t_hot = (rm.mode == kRowOneHot) ? inv_den * rm.omega : 0.f;
+            const float coef = live ? rm.omega / s : 0.f;
+            const float t_all = (rm.mode == kRowUniform) ? a.t_uniform : 0.f;
+            const float t_hot = (rm.mode == kRowOneHot) ? rm.omega : 0.f;
             __nv_bfloat16* drow = dz + (int64_t)row * lddz;
+            __nv_bfloat16* drow_lo = a.dz_planes > 1 ? drow + (int64_t)a.B * lddz : nullptr;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 if (j < nj) {
@@ -1428,9 +1355,21 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                             uint2 u;
                             u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
                             *reinterpret_cast<uint2*>(drow + col0) = u;
+                            if (drow_lo) {
+                                const float2 h0 = __bfloat1622float2(p0), h1 = __bfloat1622float2(p1);
+                                __nv_bfloat162 q0 = __floats2bfloat162_rn(g[0] - h0.x, g[1] - h0.y), q1 = __floats2bfloat162_rn(g[2] - h1.x, g[3] - h1.y);
+                                u.x = *reinterpret_cast<uint32_t*>(&q0); u.y = *reinterpret_cast<uint32_t*>(&q1);
+                                *reinterpret_cast<uint2*>(drow_lo + col0) = u;
+                            }
                         } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) if (col0 + e < a.C) drow[col0 + e] = __float2bfloat16_rn(g[e]);
+                            for (int e = 0; e < 4; ++e) {
+                                if (col0 + e < a.C) {
+                                    const __nv_bfloat16 hi = __float2bfloat16_rn(g[e]);
+                                    drow[col0 + e] = hi;
+                                    if (drow_lo) drow_lo[col0 + e] = __float2bfloat16_rn(g[e] - __bfloat162float(hi));
+                                }
+                            }
                         }
                     }
                 }
@@ -1475,7 +1414,10 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 tot = warp_sum(tot);
                 if (lane == 0) {
                     a.loss_num[0] = tot;
-                    a.loss[0] = (float)(tot / a.den[0]);
+                    // Launched with programmatic stream serialization behind the kernel that writes den
+                    // (OSB_FWD_DEN_FROM_PREV_KERNEL), this grid has run under it: wait for it only now
+                    if (a.den_from_prev) pdl_wait();
+                    a.loss[0] = a.den ? (float)(tot / a.den[0]) : (float)tot;
                     *a.ticket = 0u;
                 }
             }
@@ -1490,13 +1432,12 @@ head_fwd_splitk_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 }
 
 // ---- host --------------------------------------------------------------------------------------
-static int g_head_pairs = 1;          // 1: GEMMs run on CTA pairs (cta_group::2) where a pair kernel exists; 0: single-CTA kernels
 // the dW GEMM runs on CTA pairs (256 classes per pair) when the head is wider than one single-CTA tile
-static bool dw_pairs(int C) { return g_head_pairs != 0 && C > BM; }
+static bool dw_pairs(int C) { return C > BM; }
 
 // split-K factor of the dW GEMM: output tiles x splits fill the SMs (pairs) once
-static int dw_splits(int B, int K, int C, int force_pair = -1) {
-    const bool pair = force_pair < 0 ? dw_pairs(C) : (force_pair != 0 && C > BM);
+static int dw_splits(int B, int K, int C) {
+    const bool pair = dw_pairs(C);
     const int mt = pair ? (C + 255) / 256 : (C + BM - 1) / BM, nt = (K + kDwBN - 1) / kDwBN;
     const int kb_total = (B + BK - 1) / BK;
     int sms = sm_count();
@@ -1520,13 +1461,13 @@ static int set_smem(KernelT kernel, int bytes) {
     return OSB_OK;
 }
 
-template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED>
+template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED, bool PLANES2>
 static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
-                        cudaStream_t st) {
+                        int max_ctas, cudaStream_t st) {
     using Cfg = FwdCfg<BN, CL, STAGES, EW, PAIR>;
     constexpr int kCtasPerGroup = CL * (PAIR ? 2 : 1);
     const int n_tiles = (a.B + Cfg::kTileRows - 1) / Cfg::kTileRows;
-    auto k = head_fwd_kernel<BN, CL, STAGES, EW, PAIR, HAS_BIAS, WANT_PRED>;
+    auto k = head_fwd_kernel<BN, CL, STAGES, EW, PAIR, HAS_BIAS, WANT_PRED, PLANES2>;
     int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -1545,7 +1486,7 @@ static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
         attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    int groups = cta_limit() / kCtasPerGroup;
+    int groups = cta_limit(max_ctas) / kCtasPerGroup;
     if (groups * (PAIR ? 2 : 1) > kMaxXid) groups = kMaxXid / (PAIR ? 2 : 1);
     if (groups < 1) groups = 1;
     // every group runs ceil(n_tiles / groups) rounds: use the fewest groups that keep that round count (the others
@@ -1557,18 +1498,20 @@ static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
     return OSB_OK;
 }
 
-template <int BN, int CL, int STAGES, int EW, bool PAIR>
+template <int BN, int CL, int STAGES>
 static int launch_fwd(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
-                      cudaStream_t st) {
+                      int max_ctas, cudaStream_t st) {
     const bool pred = a.row_pred || a.row_pmax_all;
-    if (a.bias) return pred ? launch_fwd_k<BN, CL, STAGES, EW, PAIR, true, true>(tx, tw, tdz, a, st)
-                            : launch_fwd_k<BN, CL, STAGES, EW, PAIR, true, false>(tx, tw, tdz, a, st);
-    return pred ? launch_fwd_k<BN, CL, STAGES, EW, PAIR, false, true>(tx, tw, tdz, a, st)
-                : launch_fwd_k<BN, CL, STAGES, EW, PAIR, false, false>(tx, tw, tdz, a, st);
+    const bool two = a.write_dz && a.dz_planes > 1;
+#define OSB_FWD(BIAS_, PRED_) (two ? launch_fwd_k<BN, CL, STAGES, 2, true, BIAS_, PRED_, true>(tx, tw, tdz, a, max_ctas, st) \
+                                   : launch_fwd_k<BN, CL, STAGES, 2, true, BIAS_, PRED_, false>(tx, tw, tdz, a, max_ctas, st))
+    if (a.bias) return pred ? OSB_FWD(true, true) : OSB_FWD(true, false);
+    return pred ? OSB_FWD(false, true) : OSB_FWD(false, false);
+#undef OSB_FWD
 }
 
-// rows of the W box one CTA stages per k-block
-static int fwd_box_rows(int C, bool pair) { return (C <= 128 ? 128 : 256) / (pair ? 2 : 1); }
+// rows of the W box one CTA of a pair stages per k-block
+static int fwd_box_rows(int C) { return (C <= 128 ? 128 : 256) / 2; }
 
 }  // namespace head
 }  // namespace osb
@@ -1576,14 +1519,7 @@ static int fwd_box_rows(int C, bool pair) { return (C <= 128 ? 128 : 256) / (pai
 using namespace osb;
 using namespace osb::head;
 
-// developer hook (not part of the public header): A/B switch between the single-CTA and the CTA-pair kernels
-extern "C" void osb_debug_set_head_pairs(int on) { g_head_pairs = on; }
-// osb_head_forward_after_labels(1): the caller promises that the kernel in front of the next osb_head_forward calls on
-// their stream is osb_label_stats (whose own predecessor has completed): the split-K forward is then launched with
-// programmatic stream serialization and loads its operands while the label statistics still run.
-static thread_local int g_fwd_after_labels = 0;
-extern "C" int osb_head_forward_after_labels(int on) { const int old = g_fwd_after_labels; g_fwd_after_labels = on ? 1 : 0; return old; }
-// developer hook: 0 sends small batches through the persistent kernels too (A/B reference of the split-K forward)
+// developer hook (osb_debug.h): 0 sends small batches through the persistent kernels too (A/B reference of the split-K forward)
 static int g_head_splitk = 1;
 extern "C" void osb_debug_set_head_splitk(int on) { g_head_splitk = on; }
 // the split-K forward takes batches whose 128-row tiles x 8 CTAs fit the GPU at once (B <= 2048), heads of one tile
@@ -1609,16 +1545,19 @@ static int splitk_max_clusters() {
     return cached;
 }
 extern "C" int osb_debug_head_splitk_max_clusters(void) { return splitk_max_clusters(); }
-static bool fwd_use_splitk(int64_t B, int K, int C) {
+static bool fwd_use_splitk(int64_t B, int K, int C, int max_ctas) {
     if (!g_head_splitk || C > kSkBN || K < BK * kSkS) return false;
     const int64_t tiles = (B + BM - 1) / BM;
-    return tiles * kSkS <= cta_limit() && tiles <= splitk_max_clusters();
+    return tiles * kSkS <= cta_limit(max_ctas) && tiles <= splitk_max_clusters();
 }
-static thread_local bool g_dw_partials_only = false;   // set by osb_head_backward_dw_partials around its call
+extern "C" int osb_head_forward_is_splitk(int64_t B, int K, int C) {
+    if (osb::check_device() != OSB_OK) return 0;
+    return fwd_use_splitk(B, K, C, 0) ? 1 : 0;
+}
 static long long* g_trace = nullptr;
 static int g_dbg = 0;
 extern "C" void osb_debug_set_head_dbg(int v) { g_dbg = v; }
-// developer hook (not part of the public header): device buffer of [grid][64] int64 clock stamps, or NULL
+// developer hook (osb_debug.h): device buffer of [grid][64] int64 clock stamps, or NULL
 extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<long long*>(p); }
 
 // launch configuration with programmatic stream serialization: the kernel's prologue may overlap the tail of the kernel in
@@ -1636,10 +1575,7 @@ static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
 
 extern "C" size_t osb_head_workspace_bytes(int64_t B, int K, int C) {
     if (B < 0 || K <= 0 || C <= 0) return 0;
-    // room for either GEMM path (the developer switch may change after the caller sized its workspace)
-    const int s0 = dw_splits((int)B, K, C, 0), s1 = dw_splits((int)B, K, C, 1);
-    const int s = s0 > s1 ? s0 : s1;
-    return kWsOffDw + align_up((size_t)s * C * K * sizeof(float), 256) + 256;
+    return kWsOffDw + align_up((size_t)dw_splits((int)B, K, C) * C * K * sizeof(float), 256) + 256;
 }
 
 #define OSB_TMAP(call, what)                                                              \
@@ -1664,26 +1600,30 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
                                 int64_t ignore_index, const double* den, int valid_cols,
                                 double* loss_num, float* loss,
                                 float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
-                                void* dz, int64_t lddz, void* ws, size_t ws_bytes, void* stream) {
+                                void* dz, int64_t lddz, int dz_planes, int flags, int max_ctas,
+                                void* ws, size_t ws_bytes, void* stream) {
     OSB_ENTRY_GUARD();
-    OSB_REQUIRE(x && w && y && den && loss_num && loss && ws, OSB_ERR_ARG, "osb_head_forward: null pointer");
+    OSB_REQUIRE(x && w && y && loss_num && loss && ws, OSB_ERR_ARG, "osb_head_forward: null pointer");
     int rc = check_head_shapes("osb_head_forward", B, K, C, ldx);
     if (rc) return rc;
     OSB_REQUIRE(variant >= OSB_ENTROPIC && variant <= OSB_GARBAGE, OSB_ERR_ARG, "osb_head_forward: bad variant %d", variant);
     OSB_REQUIRE(variant != OSB_GARBAGE || class_w, OSB_ERR_ARG, "osb_head_forward: garbage variant needs class_w");
     OSB_REQUIRE(valid_cols >= 1 && valid_cols <= C, OSB_ERR_ARG, "osb_head_forward: valid_cols=%d outside [1,%d]", valid_cols, C);
     OSB_REQUIRE(!dz || (lddz >= C && lddz % 8 == 0), OSB_ERR_ARG, "osb_head_forward: lddz=%lld must be >= C and a multiple of 8", (long long)lddz);
+    OSB_REQUIRE(!dz || dz_planes == 1 || dz_planes == 2, OSB_ERR_ARG, "osb_head_forward: dz_planes=%d must be 1 or 2", dz_planes);
+    OSB_REQUIRE(max_ctas >= 0 && (flags & ~OSB_FWD_DEN_FROM_PREV_KERNEL) == 0, OSB_ERR_ARG, "osb_head_forward: bad flags / max_ctas");
+    OSB_REQUIRE(!(flags & OSB_FWD_DEN_FROM_PREV_KERNEL) || den, OSB_ERR_ARG, "osb_head_forward: OSB_FWD_DEN_FROM_PREV_KERNEL without den");
     OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)dz % 16 == 0), OSB_ERR_ARG,
                 "osb_head_forward: x, w and dz must be 16-byte aligned");
     OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "osb_head_forward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tx, tw;
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, BM), "x");
-    const bool pair = g_head_pairs != 0;
-    const bool splitk = fwd_use_splitk(B, K, C);
-    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, splitk ? (uint32_t)((C + 15) & ~15) : (uint32_t)fwd_box_rows(C, pair)), "w");
+    const bool splitk = fwd_use_splitk(B, K, C, max_ctas);
+    OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, splitk ? (uint32_t)((C + 15) & ~15) : (uint32_t)fwd_box_rows(C)), "w");
     CUtensorMap tdz = tx;       // placeholder when no grad-logits are written
-    if (dz && !splitk) OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 32), "dz (store)");
+    if (dz && !splitk)
+        OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)dz_planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, 32), "dz (store)");
     FwdArgs a;
     a.bias = bias; a.y = y; a.class_w = class_w; a.B = (int)B; a.K = K; a.C = C; a.variant = variant;
     a.t_uniform = (float)(unk_weight / (double)C);
@@ -1691,6 +1631,8 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.loss_num = loss_num; a.loss = loss;
     a.row_ptgt = row_ptgt; a.row_pmax = row_pmax; a.row_pmax_all = row_pmax_all; a.row_pred = row_pred;
     a.write_dz = dz ? 1 : 0;
+    a.dz_planes = dz ? dz_planes : 1;
+    a.den_from_prev = 0;
     a.ticket = reinterpret_cast<unsigned int*>(ws);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kWsOffPartials);
     a.xch_epoch = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffEpoch);
@@ -1706,7 +1648,9 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = g_fwd_after_labels ? 1 : 0;      // the cluster shape is a compile-time attribute of the kernel
+        static const bool no_pdl = getenv("OSB_NO_PDL") != nullptr;
+        a.den_from_prev = ((flags & OSB_FWD_DEN_FROM_PREV_KERNEL) && !no_pdl) ? 1 : 0;
+        cfg.numAttrs = a.den_from_prev;                 // the cluster shape is a compile-time attribute of the kernel
         __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dz);
         if (bias) {
             rc = set_smem(head_fwd_splitk_kernel<true>, kSkSmemBytes); if (rc) return rc;
@@ -1717,93 +1661,108 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
         }
         return OSB_OK;
     }
-    if (pair) {
-        if (C <= 128) return launch_fwd<128, 1, 6, 2, true>(tx, tw, tdz, a, st);
-        if (C <= 256) return launch_fwd<256, 1, 4, 2, true>(tx, tw, tdz, a, st);
-        if (C <= 512) return launch_fwd<256, 2, 4, 2, true>(tx, tw, tdz, a, st);
-        if (C <= 768) return launch_fwd<256, 3, 4, 2, true>(tx, tw, tdz, a, st);
-        return launch_fwd<256, 4, 4, 2, true>(tx, tw, tdz, a, st);
-    }
-    if (C <= 128) return launch_fwd<128, 1, 4, 2, false>(tx, tw, tdz, a, st);
-    if (C <= 256) return launch_fwd<256, 1, 3, 2, false>(tx, tw, tdz, a, st);
-    if (C <= 512) return launch_fwd<256, 2, 3, 2, false>(tx, tw, tdz, a, st);
-    if (C <= 768) return launch_fwd<256, 3, 3, 2, false>(tx, tw, tdz, a, st);
-    return launch_fwd<256, 4, 3, 2, false>(tx, tw, tdz, a, st);
+    // the persistent kernel is launched in plain stream order: den (if any) is complete when it starts
+    if (C <= 128) return launch_fwd<128, 1, 6>(tx, tw, tdz, a, max_ctas, st);
+    if (C <= 256) return launch_fwd<256, 1, 4>(tx, tw, tdz, a, max_ctas, st);
+    if (C <= 512) return launch_fwd<256, 2, 4>(tx, tw, tdz, a, max_ctas, st);
+    if (C <= 768) return launch_fwd<256, 3, 4>(tx, tw, tdz, a, max_ctas, st);
+    return launch_fwd<256, 4, 4>(tx, tw, tdz, a, max_ctas, st);
 }
 
-extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w,
-                                 int64_t B, int K, int C, const float* gscale,
-                                 void* dx, int64_t lddx, float* dw, float* db,
+// the dW GEMM (split-K partials into the workspace); returns the split count through *splits_out
+static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, int64_t ldx, int64_t B, int K, int C,
+                       void* ws, cudaStream_t st, int* splits_out) {
+    CUtensorMap tdz, tx;
+    OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, 64), "dz (MN-major)");
+    OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
+    const int splits = dw_splits((int)B, K, C);
+    *splits_out = splits;
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
+    cudaLaunchAttribute pdl_attr;
+    int rc;
+    if (dw_pairs(C)) {
+        rc = set_smem(head_dw2_kernel, kDw2SmemBytes);
+        if (rc) return rc;
+        const int units = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN) * splits;
+        CUtensorMap tpart;
+        OSB_TMAP(make_tmap_f32_3d(&tpart, partials, (uint64_t)splits, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW partials (store)");
+        cudaLaunchConfig_t cfg = pdl_config(dim3(units * 2), dim3(kThreads), kDw2SmemBytes, st, &pdl_attr);
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, (int)B, K, C, planes, splits, g_trace));
+    } else {
+        rc = set_smem(head_dw_kernel, kDwSmemBytes);
+        if (rc) return rc;
+        const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
+        cudaLaunchConfig_t cfg = pdl_config(dim3(units), dim3(kThreads), kDwSmemBytes, st, &pdl_attr);
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw_kernel, tdz, tx, (int)B, K, C, planes, splits, partials));
+    }
+    return OSB_OK;
+}
+
+static int check_backward_args(const char* fn, const void* dz, int64_t lddz, int planes, const void* x, int64_t ldx,
+                               int64_t B, int K, int C, const void* ws, size_t ws_bytes) {
+    OSB_REQUIRE(dz && x && ws, OSB_ERR_ARG, "%s: null pointer", fn);
+    int rc = check_head_shapes(fn, B, K, C, ldx);
+    if (rc) return rc;
+    OSB_REQUIRE(lddz >= C && lddz % 8 == 0, OSB_ERR_ARG, "%s: lddz=%lld must be >= C and a multiple of 8", fn, (long long)lddz);
+    OSB_REQUIRE(planes == 1 || planes == 2, OSB_ERR_ARG, "%s: dz_planes=%d must be 1 or 2", fn, planes);
+    OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)ws % 16 == 0), OSB_ERR_ARG,
+                "%s: x, dz and the workspace must be 16-byte aligned", fn);
+    OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "%s: workspace too small", fn);
+    return OSB_OK;
+}
+
+extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, const double* den, const void* x, int64_t ldx,
+                                 const void* w, int64_t B, int K, int C, const float* gscale,
+                                 void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas,
                                  void* ws, size_t ws_bytes, void* stream) {
     OSB_ENTRY_GUARD();
-    OSB_REQUIRE(dz && x && w && ws, OSB_ERR_ARG, "osb_head_backward: null pointer");
-    int rc = check_head_shapes("osb_head_backward", B, K, C, ldx);
+    int rc = check_backward_args("osb_head_backward", dz, lddz, dz_planes, x, ldx, B, K, C, ws, ws_bytes);
     if (rc) return rc;
-    OSB_REQUIRE(lddz >= C && lddz % 8 == 0, OSB_ERR_ARG, "osb_head_backward: lddz=%lld must be >= C and a multiple of 8", (long long)lddz);
+    OSB_REQUIRE(den, OSB_ERR_ARG, "osb_head_backward: null den");
+    OSB_REQUIRE(!dx || w, OSB_ERR_ARG, "osb_head_backward: dx needs w");
+    OSB_REQUIRE(dx_dtype == OSB_BF16 || dx_dtype == OSB_F32, OSB_ERR_ARG, "osb_head_backward: bad dx_dtype %d", dx_dtype);
     OSB_REQUIRE(!dx || (lddx >= K && lddx % 8 == 0), OSB_ERR_ARG, "osb_head_backward: bad lddx=%lld", (long long)lddx);
-    OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)dz % 16 == 0) &&
-                ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0) && ((uintptr_t)ws % 16 == 0), OSB_ERR_ARG,
-                "osb_head_backward: x, w, dz, dx and dw must be 16-byte aligned");
-    OSB_REQUIRE(ws_bytes >= osb_head_workspace_bytes(B, K, C), OSB_ERR_WORKSPACE, "osb_head_backward: workspace too small");
+    OSB_REQUIRE(((uintptr_t)w % 16 == 0) && ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0) && max_ctas >= 0, OSB_ERR_ARG,
+                "osb_head_backward: w, dx and dw must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (dx) {
         CUtensorMap tdz, tw, tdx;
-        OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, BM), "dz (K-major)");
+        OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)dz_planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, BM), "dz (K-major)");
         OSB_TMAP(make_tmap_bf16(&tw, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, 64), "w (MN-major)");
-        OSB_TMAP(make_tmap_bf16(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx");
-        if (g_head_pairs) {
-            rc = set_smem(head_dx2_kernel, kDx2SmemBytes);
+        const int total2 = (int)((B + 255) / 256) * ((K + kDxBN - 1) / kDxBN);
+        int pairs = cta_limit(max_ctas) / 2;
+        if (pairs > total2) pairs = total2;
+        if (pairs < 1) pairs = 1;
+        cudaLaunchAttribute pdl_attr;
+        cudaLaunchConfig_t cfg = pdl_config(dim3(pairs * 2), dim3(kDx2Threads), kDx2SmemBytes, st, &pdl_attr);
+        if (dx_dtype == OSB_F32) {
+            OSB_TMAP(make_tmap_f32_2d(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx (fp32)");
+            rc = set_smem(head_dx2_kernel<true>, kDx2SmemBytes);
             if (rc) return rc;
-            const int total2 = (int)((B + 255) / 256) * ((K + kDxBN - 1) / kDxBN);
-            int pairs = cta_limit() / 2;
-            if (pairs > total2) pairs = total2;
-            cudaLaunchAttribute pdl_attr;
-            cudaLaunchConfig_t cfg = pdl_config(dim3(pairs * 2), dim3(kDx2Threads), kDx2SmemBytes, st, &pdl_attr);
-            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel, tdz, tw, tdx, (int)B, K, C, gscale, g_trace, g_dbg));
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel<true>, tdz, tw, tdx, (int)B, K, C, dz_planes, gscale, den, g_trace, g_dbg));
         } else {
-            rc = set_smem(head_dx_kernel, kDxSmemBytes);
+            OSB_TMAP(make_tmap_bf16(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx");
+            rc = set_smem(head_dx2_kernel<false>, kDx2SmemBytes);
             if (rc) return rc;
-            const int total = (int)((B + BM - 1) / BM) * ((K + kDxBN - 1) / kDxBN);
-            int grid = cta_limit();
-            if (grid > total) grid = total;
-            head_dx_kernel<<<grid, kThreads, kDxSmemBytes, st>>>(tdz, tw, tdx, (int)B, K, C, gscale);
-            OSB_LAUNCH_CHECK();
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel<false>, tdz, tw, tdx, (int)B, K, C, dz_planes, gscale, den, g_trace, g_dbg));
         }
     }
-    if (dw || g_dw_partials_only) {
-        CUtensorMap tdz, tx;
-        OSB_TMAP(make_tmap_bf16(&tdz, dz, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, 64), "dz (MN-major)");
-        OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
-        const int splits = dw_splits((int)B, K, C);
-        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
+    if (dw) {
+        int splits = 1;
+        rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits);
+        if (rc) return rc;
+        const float* partials = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + kWsOffDw);
+        const size_t n4 = (size_t)C * K / 4;
+        int rgrid = (int)((n4 + 255) / 256);
+        const int cap = sm_count() * 8;
+        if (rgrid > cap) rgrid = cap;
         cudaLaunchAttribute pdl_attr;
-        if (dw_pairs(C)) {
-            rc = set_smem(head_dw2_kernel, kDw2SmemBytes);
-            if (rc) return rc;
-            const int units = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN) * splits;
-            CUtensorMap tpart;
-            OSB_TMAP(make_tmap_f32_3d(&tpart, partials, (uint64_t)splits, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW partials (store)");
-            cudaLaunchConfig_t cfg = pdl_config(dim3(units * 2), dim3(kThreads), kDw2SmemBytes, st, &pdl_attr);
-            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, (int)B, K, C, splits, g_trace));
-        } else {
-            rc = set_smem(head_dw_kernel, kDwSmemBytes);
-            if (rc) return rc;
-            const int units = ((C + BM - 1) / BM) * ((K + kDwBN - 1) / kDwBN) * splits;
-            cudaLaunchConfig_t cfg = pdl_config(dim3(units), dim3(kThreads), kDwSmemBytes, st, &pdl_attr);
-            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw_kernel, tdz, tx, (int)B, K, C, splits, partials));
-        }
-        if (dw) {
-            const size_t n4 = (size_t)C * K / 4;
-            int rgrid = (int)((n4 + 255) / 256);
-            const int cap = sm_count() * 8;
-            if (rgrid > cap) rgrid = cap;
-            cudaLaunchConfig_t cfg = pdl_config(dim3(rgrid), dim3(256), 0, st, &pdl_attr);
-            OSB_CUDA(cudaLaunchKernelEx(&cfg, dw_reduce_kernel, reinterpret_cast<const float4*>(partials), splits, n4, gscale,
-                                        reinterpret_cast<float4*>(dw)));
-        }
+        cudaLaunchConfig_t cfg = pdl_config(dim3(rgrid), dim3(256), 0, st, &pdl_attr);
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, dw_reduce_kernel, reinterpret_cast<const float4*>(partials), splits, n4, gscale, den,
+                                    reinterpret_cast<float4*>(dw)));
     }
     if (db) {
-        db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, gscale, db);
+        db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, dz_planes, gscale, den, db);
         OSB_LAUNCH_CHECK();
     }
     return OSB_OK;
@@ -1812,11 +1771,19 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, const void* x, in
 // ---- multi-GPU: the dW GEMM alone (split-K partials stay in the workspace), for the peer-memory all-reduce ----
 extern "C" size_t osb_head_dw_partials_offset(void) { return kWsOffDw; }
 extern "C" int osb_head_dw_splits(int64_t B, int K, int C) { return dw_splits((int)B, K, C); }
-extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, const void* x, int64_t ldx, int64_t B, int K, int C,
+extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
+                                             int64_t B, int K, int C, float* db_partial,
                                              void* ws, size_t ws_bytes, void* stream) {
-    g_dw_partials_only = true;
-    // w is not read by the dW GEMM; x doubles as a valid non-null placeholder for the argument checks
-    const int rc = osb_head_backward(dz, lddz, x, ldx, x, B, K, C, nullptr, nullptr, K, nullptr, nullptr, ws, ws_bytes, stream);
-    g_dw_partials_only = false;
-    return rc;
+    OSB_ENTRY_GUARD();
+    int rc = check_backward_args("osb_head_backward_dw_partials", dz, lddz, dz_planes, x, ldx, B, K, C, ws, ws_bytes);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int splits = 1;
+    rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits);
+    if (rc) return rc;
+    if (db_partial) {
+        db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, dz_planes, nullptr, nullptr, db_partial);
+        OSB_LAUNCH_CHECK();
+    }
+    return OSB_OK;
 }

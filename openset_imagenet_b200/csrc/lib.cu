@@ -56,10 +56,9 @@ int check_device() {
     return probe(dev);
 }
 
-static int g_cta_limit = 0;
-int cta_limit() {
+int cta_limit(int max_ctas) {
     const int sms = sm_count();
-    return (g_cta_limit > 0 && g_cta_limit < sms) ? g_cta_limit : sms;
+    return (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
 }
 
 int sm_count() {
@@ -75,8 +74,3 @@ extern "C" int osb_abi_version(void) { return OSB_ABI_VERSION; }
 extern "C" const char* osb_last_error(void) { return osb::g_err; }
 extern "C" int osb_device_check(void) { return osb::check_device(); }
 extern "C" int osb_sm_count(void) { return osb::sm_count(); }
-extern "C" int osb_set_cta_limit(int max_ctas) {
-    const int old = osb::g_cta_limit;
-    osb::g_cta_limit = max_ctas < 0 ? 0 : max_ctas;
-    return old;
-}

@@ -18,8 +18,8 @@ __global__ void __launch_bounds__(kLabelThreads)
 label_stats_kernel(const int64_t* __restrict__ y, const float* __restrict__ class_w, int64_t B, int C,
                    int variant, int64_t ignore_index, double* __restrict__ den_out,
                    int64_t* __restrict__ counts_out, double* partials, unsigned int* ticket) {
-    // A forward kernel launched with programmatic stream serialization (osb_head_forward_after_labels) may start its
-    // operand loads now; it waits for this grid (griddepcontrol.wait) before it reads the denominator.
+    // A forward kernel launched with programmatic stream serialization (OSB_FWD_DEN_FROM_PREV_KERNEL) may start
+    // now; it waits for this grid (griddepcontrol.wait) before it reads the denominator.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     double den = 0.0;
     long long c_onehot = 0, c_uniform = 0, c_ignored = 0, c_bad = 0;
@@ -204,7 +204,7 @@ extern "C" size_t osb_loss_workspace_bytes(int64_t B) {
 
 extern "C" int osb_label_stats(const int64_t* y, const float* class_w, int64_t B, int C, int variant,
                                int64_t ignore_index, double* den, int64_t* counts,
-                               void* ws, size_t ws_bytes, void* stream) {
+                               void* ws, size_t ws_bytes, int max_ctas, void* stream) {
     OSB_ENTRY_GUARD();
     OSB_REQUIRE(y && den && counts && ws, OSB_ERR_ARG, "osb_label_stats: null pointer");
     OSB_REQUIRE(B >= 0 && C > 0, OSB_ERR_ARG, "osb_label_stats: bad sizes B=%lld C=%d", (long long)B, C);
@@ -213,9 +213,9 @@ extern "C" int osb_label_stats(const int64_t* y, const float* class_w, int64_t B
     OSB_REQUIRE(ws_bytes >= osb_loss_workspace_bytes(B), OSB_ERR_WORKSPACE, "osb_label_stats: workspace too small");
     int grid = (int)((B + kLabelThreads - 1) / kLabelThreads);
     grid = grid < 1 ? 1 : (grid > kMaxReduceGrid ? kMaxReduceGrid : grid);
-    // osb_set_cta_limit bounds this grid too: a caller that runs the statistics beside a GEMM kernel keeps them on a few
-    // SMs (the sums are integers and the row count: the result does not depend on the grid)
-    if (grid > cta_limit()) grid = cta_limit();
+    // a caller that runs the statistics beside a GEMM kernel keeps them on a few SMs (the sums are integers and the
+    // row count: the result does not depend on the grid)
+    if (grid > cta_limit(max_ctas)) grid = cta_limit(max_ctas);
     auto* ticket = reinterpret_cast<unsigned int*>(ws);
     auto* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kTicketBytes);
     label_stats_kernel<<<grid, kLabelThreads, 0, (cudaStream_t)stream>>>(y, class_w, B, C, variant, ignore_index,

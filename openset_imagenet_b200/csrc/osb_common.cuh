@@ -8,6 +8,7 @@
 #include <stdarg.h>
 
 #include "../../include/osb.h"
+#include "../../include/osb_debug.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libosb is written for sm_100a (B200) only"
@@ -19,7 +20,7 @@ namespace osb {
 void set_error(const char* fmt, ...);
 int  check_device();                 // OSB_OK or OSB_ERR_ARCH (cached per device)
 int  sm_count();                     // cached
-int  cta_limit();                    // sm_count() or the smaller bound set by osb_set_cta_limit()
+int  cta_limit(int max_ctas);         // sm_count(), or the caller's smaller bound (max_ctas > 0)
 
 #define OSB_REQUIRE(cond, code, ...)                 \
     do {                                             \

@@ -67,6 +67,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// 3-D variant (c2 = plane): the grad-logits planes [plane][row][class]
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // global -> L2 only (no shared-memory destination, no completion): warms L2 for a tile that will be loaded later
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(m), "r"(c0), "r"(c1) : "memory");
@@ -193,6 +199,10 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // Arrive on the LEADER CTA's barrier at this offset (from either CTA of the pair).  RELAXED: the barrier only hands a TMEM
 // accumulator back to the MMA warp, and the tcgen05 loads that read it are ordered by tcgen05.wait::ld +
 // tcgen05.fence::before_thread_sync.  The default .release.cluster compiles to MEMBAR.ALL.GPU in front of the arrive,
@@ -287,6 +297,50 @@ static inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t ro
     if (r != CUDA_SUCCESS) return (int)r;
     e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.box_rows = box_rows; e.box_cols = box_cols; e.map = *out; e.valid = true;
     return 0;
+}
+
+// 3-D bf16 tensor [planes, rows, cols] (row pitch `ld`, plane pitch `plane_ld` elements); box = 64 columns x box_rows
+// rows x 1 plane, SWIZZLE_128B: the grad-logits planes (plane 1 = bf16 rounding residual of plane 0).  Cached like the
+// 2-D descriptors.
+static inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld,
+                                    uint64_t plane_ld, uint32_t box_rows) {
+    struct Entry { const void* base; uint64_t planes, rows, cols, ld, plane_ld; uint32_t box_rows; bool valid; CUtensorMap map; };
+    constexpr int kSlots = 16;
+    static thread_local Entry cache[kSlots];
+    const uint64_t h = (reinterpret_cast<uint64_t>(base) >> 8) ^ (rows * 0x9E3779B97F4A7C15ull) ^ (cols << 20) ^ (ld << 40) ^ box_rows ^ (planes << 7);
+    Entry& e = cache[(h ^ (h >> 17) ^ (h >> 31)) % kSlots];
+    if (e.valid && e.base == base && e.planes == planes && e.rows == rows && e.cols == cols && e.ld == ld && e.plane_ld == plane_ld &&
+        e.box_rows == box_rows) {
+        *out = e.map;
+        return 0;
+    }
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t dims[3] = {cols, rows, planes};
+    cuuint64_t strides[2] = {ld * 2, plane_ld * 2};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)r;
+    e.base = base; e.planes = planes; e.rows = rows; e.cols = cols; e.ld = ld; e.plane_ld = plane_ld; e.box_rows = box_rows;
+    e.map = *out; e.valid = true;
+    return 0;
+}
+
+// 2-D fp32 tensor [rows, cols] (row pitch `ld` elements); box = 32 columns (128 bytes) x box_rows rows, SWIZZLE_128B: dX in fp32
+static inline int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
 // 3-D fp32 tensor [planes, rows, cols] (row pitch `ld` elements, plane pitch rows * ld); box = 32 columns (128 bytes) x

@@ -48,14 +48,10 @@ class ShardedHead:
         self._flat = None
 
     def _global_den(self, den: torch.Tensor) -> torch.Tensor:
+        # shards may differ in size, so even the entropic row count is summed
         _, ws = world()
-        if ws == 1:
-            return den
-        if self.head.variant_name == "entropic":
-            # every row counts: the global denominator is the global batch size when shards are equal,
-            # otherwise it still needs the sum
-            pass
-        dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
+        if ws > 1:
+            dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
         return den
 
     def loss(self, features, target):
@@ -98,27 +94,30 @@ class PeerGradAllReduce:
     """The head's dW all-reduce over NVLink peer memory, fused with the split-K reduction (``osb_head_dw_allreduce``).
 
     Every pointer table lists, per rank, the DEVICE address of that rank's buffer as mapped into this process:
-    the head workspace (split-K partials), the packed ``[dW | db | loss]`` buffer, and a small flag area.
+    the head workspace (split-K partials), the packed ``[dW | db | tail]`` buffer, and a small flag area.
     ``from_symmetric_memory`` builds them with ``torch.distributed._symmetric_memory``; tests on one GPU pass
-    plain pointers.  ``run()`` enqueues ONE kernel on a side stream (after the dW GEMM of the current stream) and
-    returns an event; the result is bit-identical on every rank and deterministic.
+    plain pointers.  ``launch()`` enqueues ONE kernel on the current stream; it has no per-step argument (the epoch
+    lives in the flag area), so it can be captured into a CUDA graph.  The result is bit-identical on every rank.
+    ``extra_sum`` = [db summed and scaled like dW | plain sums of the tail (loss numerators)].
     """
 
-    def __init__(self, plan, ws_ptrs, flat_ptrs, flag_ptrs, rank, world, n_extra, max_ctas=32):
+    def __init__(self, plan, ws_ptrs, flat_ptrs, flag_ptrs, rank, world, max_ctas=32, flags_local=None):
         from . import _lib as L
         self._L = L
-        self.plan, self.rank, self.world, self.n_extra, self.max_ctas = plan, int(rank), int(world), int(n_extra), int(max_ctas)
+        self.plan, self.rank, self.world, self.max_ctas = plan, int(rank), int(world), int(max_ctas)
         off = L.size("osb_head_dw_partials_offset")
         n = plan.C * plan.K
+        self.n_extra = plan.flat.numel() - n
+        self.n_plain = plan.n_tail
         P = L.C.c_void_p * world
         self._partials = P(*[int(p) + off for p in ws_ptrs])
         self._dw = P(*[int(p) for p in flat_ptrs])
-        self._extra = P(*[int(p) + 4 * (plan.flat.numel() - n_extra) for p in flat_ptrs])
+        self._extra = P(*[int(p) + 4 * n for p in flat_ptrs])
         self._flags = P(*[int(p) for p in flag_ptrs])
+        self._flags_local = int(flag_ptrs[rank])
         self.splits = L.size("osb_head_dw_splits", plan.B, plan.K, plan.C)
         self.n = n
-        self.extra_sum = torch.zeros(max(n_extra, 1), dtype=torch.float32, device=plan.dev)
-        self.epoch = 0
+        self.extra_sum = torch.zeros(max(self.n_extra, 1), dtype=torch.float32, device=plan.dev)
         self.stream = torch.cuda.Stream(device=plan.dev)
         self._ready = torch.cuda.Event()
         self._done = torch.cuda.Event()
@@ -126,7 +125,8 @@ class PeerGradAllReduce:
 
     @classmethod
     def from_symmetric_memory(cls, B, K, C, variant, group=None, max_ctas=32, device=None, **plan_kwargs):
-        """Allocates workspace, gradient buffer and flags in symmetric memory, builds the ``HeadPlan`` on them."""
+        """Allocates workspace, gradient buffer, flags and denominator slots in symmetric memory and builds the
+        ``HeadPlan`` on them."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib as L
         from .functional import HeadPlan
@@ -134,50 +134,70 @@ class PeerGradAllReduce:
         rank, ws_ = world()
         grp = group if group is not None else dist.group.WORLD
         bias = bool(plan_kwargs.get("bias", False))
-        n_flat = C * K + (C if bias else 0) + 1
+        n_tail = int(plan_kwargs.pop("n_tail", 1))
+        n_flat = C * K + (C if bias else 0) + n_tail
         ws_bytes = max(L.size("osb_head_workspace_bytes", B, K, C), L.size("osb_loss_workspace_bytes", B)) + 4096
         wsb = symm_mem.empty(ws_bytes, dtype=torch.uint8, device=dev)
         flat = symm_mem.empty(n_flat, dtype=torch.float32, device=dev)
         flags = symm_mem.empty(L.size("osb_head_dw_allreduce_flag_bytes", ws_) // 4, dtype=torch.int32, device=dev)
-        wsb.zero_(); flat.zero_(); flags.zero_()
-        handles = [symm_mem.rendezvous(t, grp) for t in (wsb, flat, flags)]
+        slots = symm_mem.empty(L.size("osb_peer_sum_bytes", ws_) // 4, dtype=torch.int32, device=dev)
+        wsb.zero_(); flat.zero_(); flags.zero_(); slots.zero_()
+        handles = [symm_mem.rendezvous(t, grp) for t in (wsb, flat, flags, slots)]
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
-        plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=flat, workspace=wsb, **plan_kwargs)
-        obj = cls(plan, handles[0].buffer_ptrs, handles[1].buffer_ptrs, handles[2].buffer_ptrs, rank, ws_,
-                  n_extra=n_flat - C * K, max_ctas=max_ctas)
-        obj._keep = (wsb, flat, flags, handles)
+        plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=flat, workspace=wsb, n_tail=n_tail, **plan_kwargs)
+        obj = cls(plan, handles[0].buffer_ptrs, handles[1].buffer_ptrs, handles[2].buffer_ptrs, rank, ws_, max_ctas=max_ctas)
+        obj.slot_ptrs = (L.C.c_void_p * ws_)(*[int(p) for p in handles[3].buffer_ptrs])
+        obj._keep = (wsb, flat, flags, slots, handles)
         return obj
 
-    def run(self, gscale=None):
-        """dW GEMM partials must already be enqueued on the current stream.  Returns the completion event."""
+    def launch(self, den, gscale=None, stream=None):
+        """One all-reduce of the partials currently in the workspaces, on ``stream`` (default: the current one)."""
         L = self._L
+        st = L.stream_ptr(self.plan.dev) if stream is None else stream.cuda_stream
+        L.call("osb_head_dw_allreduce", self._partials, self._dw, self._extra if self.n_extra else None, self._flags,
+               self.rank, self.world, self.splits, self.n, self.n, L.ptr(self.extra_sum), self.n_extra, self.n_plain,
+               L.ptr(gscale), L.ptr(den), self.max_ctas, st)
+
+    def run(self, den, gscale=None):
+        """dW GEMM partials must already be enqueued on the current stream.  Runs the all-reduce on the side stream
+        and returns its completion event."""
         cur = torch.cuda.current_stream(self.plan.dev)
         self._ready.record(cur)
         self.stream.wait_event(self._ready)
-        self.epoch += 1
-        L.call("osb_head_dw_allreduce", self._partials, self._dw, self._extra if self.n_extra else None, self._flags,
-               self.rank, self.world, self.splits, self.n, self.n, L.ptr(self.extra_sum), self.n_extra, L.ptr(gscale),
-               self.epoch & 0xFFFFFFFF or 1, self.max_ctas, self.stream.cuda_stream)
+        self.launch(den, gscale, self.stream)
         self._done.record(self.stream)
         return self._done
 
-    def error_word(self, flags_tensor) -> int:
-        return int(flags_tensor[2 * self.world].item())
+    def failed_epoch(self) -> int:
+        """0, or the epoch at which this rank gave up waiting for a peer (host sync).  After a failure dW was NOT
+        written and the summed loss is NaN."""
+        L = self._L
+        out = L.C.c_uint32(0)
+        L.call("osb_head_dw_allreduce_error", self._flags_local, self.world, L.C.byref(out))
+        return int(out.value)
+
+    def check(self) -> None:
+        ep = self.failed_epoch()
+        if ep:
+            raise RuntimeError(f"rank {self.rank}: gradient all-reduce gave up waiting for a peer at epoch {ep}; "
+                               "gradients of that step were not written")
 
 
 class ShardedHeadPlan:
-    """Allocation-free batch-sharded head step (``functional.HeadPlan`` per rank + ONE all-reduce).
+    """Allocation-free batch-sharded head step (``functional.HeadPlan`` per rank + ONE all-reduce), capturable as ONE
+    CUDA graph per input buffer (``capture``).
 
-    The kernels write dW, db and this shard's loss contribution straight into one packed float32 buffer
-    ``flat = [dW | db | loss]``; after the dW GEMM that buffer is all-reduced asynchronously while the dX GEMM
-    (local, needs no communication) runs on ``SMs - sm_reserve`` CTAs so that the collective finds free SMs.
-    Denominator of the global mean: the entropic loss counts every row, so with equal shards it is
-    ``B_local * world`` and needs no communication; the softmax / garbage variants all-reduce one double before
-    the forward kernel.
+    The kernels write dW partials, db and this shard's loss numerator into peer-mapped buffers; the all-reduce kernel
+    sums them over NVLink, divides by the GLOBAL denominator and leaves the full-batch dW / db on every rank, while the dX
+    GEMM (local, needs no communication) runs on ``SMs - sm_reserve`` CTAs so that the collective finds free SMs.
+    Denominator of the global mean: the entropic loss counts every row, so with equal shards it is ``B_local * world``
+    and needs no communication; the softmax / garbage variants sum one double over the ranks through peer memory
+    (``osb_peer_sum``) on a branch beside the forward kernel, whose grad-logits do not depend on it.
+    Without symmetric memory (``peer_allreduce=False``) the same step runs eagerly with NCCL collectives.
     """
 
-    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=32, device=None, peer_allreduce=False,
+    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=16, device=None, peer_allreduce=False,
                  **plan_kwargs):
         from . import _lib as L
         from .functional import HeadPlan
@@ -186,6 +206,7 @@ class ShardedHeadPlan:
         self.variant = variant
         bias = bool(plan_kwargs.get("bias", False))
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
         self.peer = None
         if peer_allreduce and self.world > 1:
             # dW all-reduce over NVLink peer memory fused with the split-K reduction (no NCCL on the data path)
@@ -199,79 +220,128 @@ class ShardedHeadPlan:
         self._L = L
         self._sms = L.size("osb_sm_count")
         self.sm_reserve = int(sm_reserve) if self.world > 1 else 0
-        self._den_global = None
-        self.launches_per_step = self.plan.launches_per_step      # our kernels only (the collective is NCCL's)
-
-    def _den_hook(self, den):
-        if self.world == 1:
-            return
-        if self.variant == "entropic":
-            den.mul_(self.world)                     # every row counts and shards are equal: no communication
-        else:
-            dist.all_reduce(den, op=dist.ReduceOp.SUM, group=self.group)
-
-    def step(self, x, w, y, bias=None):
-        """Returns the async work handle of the gradient all-reduce (None on one GPU); ``finish(work)`` makes the
-        current stream wait for it.  After that ``plan.dw`` / ``plan.db`` hold the full-batch gradients and
-        ``plan.loss`` the full-batch loss on every rank; ``plan.dx`` is this shard's d loss / d features."""
         p = self.plan
-        late_labels = self.begin(x, w, y, bias)
+        self.entropic = variant == "entropic"
+        # global denominator: a constant for the entropic loss, the peer / NCCL sum of the shard denominators otherwise
+        self.den_global = (torch.full((1,), float(p.B * self.world), dtype=torch.float64, device=dev) if self.entropic
+                           else torch.zeros(1, dtype=torch.float64, device=dev))
+        self._lbranch = torch.cuda.Stream(device=dev)
+        self._abranch = torch.cuda.Stream(device=dev)
+        # our kernels per step: label statistics, forward, dW GEMM, dX, and the split-K reduce (NCCL path) or the peer
+        # all-reduce that replaces it (+ the denominator's peer sum for softmax / garbage, + db with a bias)
+        self.launches_per_step = 5 + (1 if bias else 0) + (1 if (self.peer is not None and not self.entropic) else 0)
+
+    # ---- one step; every call below only ENQUEUES, so the same body runs eagerly or under stream capture ----
+    def _body(self, x, w, y, bias=None, marks=None):
+        p, L = self.plan, self._L
+        cur = torch.cuda.current_stream(self.dev)
+        mark = (lambda i: marks[i].record(cur)) if marks is not None else (lambda i: None)
+        dx_ctas = self._sms - self.sm_reserve if self.world > 1 else 0
         if self.peer is not None:
+            # branch: label statistics (+ the denominator's sum over the ranks) beside the forward kernel
+            self._lbranch.wait_stream(cur)
+            with torch.cuda.stream(self._lbranch):
+                p.label_stats(y, max_ctas=8)
+                if not self.entropic:
+                    L.call("osb_peer_sum", L.ptr(p.den), L.ptr(self.den_global), 1, self.peer.slot_ptrs, self.rank, self.world,
+                           self._lbranch.cuda_stream)
+            mark(0)
+            p.forward(x, w, y, bias, want_pred=False, den=None)        # training step: no per-row predictions
+            mark(1)
             p.backward_dw_partials(x)
-            done = self.peer.run()
-            self._L.load().osb_set_cta_limit(self._sms - self.sm_reserve)
-            try:
-                p.backward_dx(x, w)
-            finally:
-                self._L.load().osb_set_cta_limit(0)
-            self.end(y, late_labels)
-            return done
-        p.backward_dw(x, w)
+            mark(2)
+            self._abranch.wait_stream(cur)
+            if not self.entropic:
+                self._abranch.wait_stream(self._lbranch)
+                cur.wait_stream(self._lbranch)
+            self.peer.launch(self.den_global, stream=self._abranch)
+            p.backward_dx(x, w, den=self.den_global, max_ctas=dx_ctas)
+            mark(3)
+            cur.wait_stream(self._abranch)
+            cur.wait_stream(self._lbranch)
+            return None
+        # NCCL path (eager only): the denominator first, then one all-reduce of the packed [dW | db | loss] buffer
+        p.label_stats(y)
+        if not self.entropic:
+            self.den_global.copy_(p.den)
+            if self.world > 1:
+                dist.all_reduce(self.den_global, op=dist.ReduceOp.SUM, group=self.group)
+        mark(0)
+        p.forward(x, w, y, bias, want_pred=False, den=self.den_global)
+        mark(1)
+        p.backward_dw(x, w, den=self.den_global)
+        mark(2)
         work = None
         if self.world > 1:
             work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._L.load().osb_set_cta_limit(self._sms - self.sm_reserve)
-        try:
-            p.backward_dx(x, w)
-        finally:
-            if self.world > 1:
-                self._L.load().osb_set_cta_limit(0)
-        self.end(y, late_labels)
+        p.backward_dx(x, w, den=self.den_global, max_ctas=dx_ctas)
+        mark(3)
         return work
 
-    def begin(self, x, w, y, bias=None, mark=None) -> bool:
-        """Label statistics + forward.  The entropic loss divides by the global row count (every row counts, shards are
-        equal), known without reading the labels: the forward kernel takes that constant and the statistics kernel
-        (counts for the caller, the same denominator) moves behind the GEMMs (``end``), off the head of the dependency
-        chain.  The softmax / garbage variants need the all-reduced sum of weights first.  Returns whether ``end`` has
-        the statistics left to do.  ``mark`` (bench.py) is called right before the forward launch."""
-        p = self.plan
-        late = self.variant == "entropic"
-        if late and self._den_global is None:
-            self._den_global = torch.full((1,), float(p.B * self.world), dtype=torch.float64, device=p.dev)
-        if not late:
-            p.label_stats(y, self._den_hook)
-        if mark is not None:
-            mark()
-        p.forward(x, w, y, bias, want_pred=False, den=self._den_global if late else None)   # training step: no per-row predictions
-        return late
-
-    def end(self, y, late_labels: bool) -> None:
-        if late_labels:
-            self.plan.label_stats(y, self._den_hook, ws=self.plan.ws_label)
+    def step(self, x, w, y, bias=None, marks=None):
+        """Enqueue one step.  Returns the async NCCL work handle (NCCL path) or None; ``finish(work)`` makes the
+        current stream wait for it.  After that ``plan.dw`` / ``plan.db`` hold the full-batch gradients on every rank
+        and ``full_loss()`` the full-batch loss; ``plan.dx`` is this shard's d loss / d features."""
+        return self._body(x, w, y, bias, marks)
 
     def finish(self, work):
-        """Make the current stream wait for the gradient all-reduce.  With the peer-memory path the full-batch loss
-        is ``peer.extra_sum[-1]`` (``plan.loss`` keeps this shard's contribution)."""
-        if work is None:
-            return
-        if isinstance(work, torch.cuda.Event):
-            torch.cuda.current_stream(self.plan.dev).wait_event(work)
-        else:
+        if work is not None:
             work.wait()
 
+    def capture(self, x, w, y, bias=None):
+        """The whole sharded step on (x, w, y) as ONE CUDA graph (peer-memory path): every rank must replay the same
+        number of times."""
+        if self.world > 1 and self.peer is None:
+            raise RuntimeError("capture needs the peer-memory all-reduce (NCCL collectives of the fallback path are not captured)")
+        p = self.plan
+        p._check(x, w, y)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._body(x, w, y, bias)            # warm-up outside capture; also one epoch of the collective on every rank
+            side.synchronize()
+            self._lbranch.synchronize(); self._abranch.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self._body(x, w, y, bias)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        return graph
+
     def full_loss(self) -> torch.Tensor:
-        return self.peer.extra_sum[self.peer.n_extra - 1] if self.peer is not None else self.plan.loss[0]
+        """Full-batch loss (0-dim float64 device tensor): summed numerators over the global denominator."""
+        if self.peer is not None:
+            return self.peer.extra_sum[self.peer.n_extra - 1].double() / self.den_global[0]
+        return self.plan.loss[0].double()
+
+    def db_full(self):
+        """Full-batch bias gradient (None without a bias)."""
+        if self.plan.db is None:
+            return None
+        return self.peer.extra_sum[:self.plan.C] if self.peer is not None else self.plan.db
+
+    def check(self) -> None:
+        if self.peer is not None:
+            self.peer.check()
+
+
+def confidence_sharded(scores, target_labels, offset=0., unknown_class=-1, last_valid_class=None, group=None):
+    """``metrics.confidence`` (metrics.py:8-42) over a row-sharded validation set: every rank passes ITS rows and
+    receives the tuple of the whole set.  The two float64 sums and the two counts are additive across shards
+    (SURVEY 8e): one all-reduce of four numbers."""
+    from .metrics import confidence_sums, finish_confidence
+    sums, counts = confidence_sums(scores, target_labels, offset, unknown_class, last_valid_class)
+    return finish_confidence(*allreduce_confidence(sums, counts, group), scores.shape[1])
+
+
+def allreduce_confidence(sums: torch.Tensor, counts: torch.Tensor, group=None):
+    """Sum the (float64 sums [2], int64 counts [3]) pair of ``metrics.confidence_sums`` / ``StreamingConfidence`` over
+    the ranks.  The counts travel as float64 in the same buffer (exact below 2^53)."""
+    _, ws = world()
+    if ws == 1:
+        return sums, counts
+    buf = torch.cat([sums.double(), counts.double()])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf[:2], buf[2:].round().to(torch.int64)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -14,28 +14,49 @@ _VARIANTS = {"entropic": L.ENTROPIC, "softmax": L.SOFTMAX, "garbage": L.GARBAGE}
 _DEFAULT_IGNORE = {"entropic": -100, "softmax": -1, "garbage": -100}
 
 
+def resolve_planes(precision: str, C: int, bias: bool) -> int:
+    """dZ planes for a precision policy.  'exact' keeps the bf16 rounding residual of the grad-logits in a second plane
+    (gradients within ~1e-5 of float64 at twice the backward MMA count); 'fast' is a single bf16 plane (~1e-3 norm-wise
+    in dW / dX, more in db, whose column sums cancel); 'auto' is exact where it is free -- the launch-latency-bound
+    protocol heads (C <= 256) -- and wherever a bias gradient is wanted."""
+    if precision == "exact":
+        return 2
+    if precision == "fast":
+        return 1
+    if precision == "auto":
+        return 2 if (C <= 256 or bias) else 1
+    raise ValueError(f"precision must be 'auto', 'fast' or 'exact', got {precision!r}")
+
+
 class HeadPlan:
     """Buffers + launch arguments for linear(K -> C) + open-set loss + backward on a fixed batch size.
 
     Outputs (device tensors, overwritten by every call):
       loss [1] f32, loss_num [1] f64, den [1] f64, label_counts [4] i64,
       p_target / p_max / p_max_all [B] f32, pred [B] i32,
-      dz [B, round_up(C,8)] bf16, dx [B, K] bf16, dw [C, K] f32, db [C] f32 (when bias).
+      dz [planes, B, round_up(C,8)] bf16 (denominator-free grad-logits; plane 1 = bf16 rounding residual of plane 0),
+      dx [B, K] bf16 or f32, dw [C, K] f32, db [C] f32 (when bias).
     """
 
     def __init__(self, B: int, K: int, C: int, variant: str = "entropic", unk_weight: float = 1.0,
                  class_weights: torch.Tensor | None = None, ignore_index: int | None = None,
                  last_valid_class=None, bias: bool = False, device=None, grad_buffer: torch.Tensor | None = None,
-                 workspace: torch.Tensor | None = None):
+                 workspace: torch.Tensor | None = None, precision: str = "auto", dx_dtype: torch.dtype = torch.bfloat16,
+                 n_tail: int = 1):
         if K % 64 != 0:
             raise ValueError("HeadPlan needs in_features % 64 == 0 (FusedOpenSetHead pads other widths)")
+        if dx_dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("dx_dtype must be torch.bfloat16 or torch.float32")
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.B, self.K, self.C = int(B), int(K), int(C)
+        self.variant_name = variant
         self.variant = _VARIANTS[variant]
         self.unk_weight = float(unk_weight)
         self.ignore_index = int(_DEFAULT_IGNORE[variant] if ignore_index is None else ignore_index)
         self.valid_cols = len(range(C)[slice(None, last_valid_class)])
         self.class_w = None if class_weights is None else class_weights.detach().to(self.dev).float().contiguous()
+        self.planes = resolve_planes(precision, C, bias)
+        self.dx_dtype = dx_dtype
         d = self.dev
         self.lddz = (C + 7) // 8 * 8
         ws_bytes = max(L.size("osb_head_workspace_bytes", B, K, C), L.size("osb_loss_workspace_bytes", B)) + 4096
@@ -46,29 +67,35 @@ class HeadPlan:
         self.ws = workspace
         self.ws_bytes_needed = ws_bytes
         self.den = torch.empty(1, dtype=torch.float64, device=d)
-        # entropic loss: the denominator is the row count (losses.py:29), known without reading the labels, so a captured
-        # step takes the label statistics off the critical path (own workspace: it may run beside the GEMM kernels)
+        # entropic loss: the denominator is the row count (losses.py:29), known without reading the labels
         self.den_const = torch.full((1,), float(B), dtype=torch.float64, device=d)
+        # the label statistics have their own workspace: they may run beside the forward kernel
         self.ws_label = torch.zeros(L.size("osb_loss_workspace_bytes", B) + 256, dtype=torch.uint8, device=d)
         self.label_counts = torch.empty(4, dtype=torch.int64, device=d)
-        # [dW | db | loss] may live in one caller-owned float32 buffer (the packed all-reduce buffer of dist.py), so
-        # that the kernels write straight into it and no gather copy is needed
-        n_flat = C * K + (C if bias else 0) + 1
+        # [dW | db | tail] may live in one caller-owned float32 buffer (the packed all-reduce buffer of dist.py), so
+        # that the kernels write straight into it and no gather copy is needed; tail[0] is the loss
+        n_flat = C * K + (C if bias else 0) + int(n_tail)
         if grad_buffer is None:
             grad_buffer = torch.empty(n_flat, dtype=torch.float32, device=d)
         if grad_buffer.dtype != torch.float32 or grad_buffer.numel() < n_flat or not grad_buffer.is_contiguous():
             raise ValueError(f"grad_buffer must be a contiguous float32 tensor with at least {n_flat} elements")
         self.flat = grad_buffer[:n_flat]
-        self.loss = self.flat[n_flat - 1:]
+        self.n_tail = int(n_tail)
+        self.loss = self.flat[n_flat - self.n_tail:n_flat - self.n_tail + 1]
         self.loss_num = torch.empty(1, dtype=torch.float64, device=d)
         self.stats = torch.empty(3, B, dtype=torch.float32, device=d)
         self.p_target, self.p_max, self.p_max_all = self.stats[0], self.stats[1], self.stats[2]
         self.pred = torch.empty(B, dtype=torch.int32, device=d)
-        self.dz = torch.empty(B, self.lddz, dtype=torch.bfloat16, device=d)
-        self.dx = torch.empty(B, K, dtype=torch.bfloat16, device=d)
+        self.dz = torch.empty(self.planes, B, self.lddz, dtype=torch.bfloat16, device=d)
+        self.dx = torch.empty(B, K, dtype=dx_dtype, device=d)
         self.dw = self.flat[:C * K].view(C, K)
         self.db = self.flat[C * K:C * K + C] if bias else None
         self.launches_per_step = 5 + (1 if bias else 0)   # label_stats, fwd, dx, dw, dw-reduce (+ db)
+
+    @property
+    def den_step(self) -> torch.Tensor:
+        """The denominator the kernels of a single-GPU step divide by."""
+        return self.den_const if self.variant == L.ENTROPIC else self.den
 
     def _check(self, x, w, y):
         if x.shape != (self.B, self.K) or x.dtype != torch.bfloat16 or not x.is_contiguous():
@@ -78,30 +105,43 @@ class HeadPlan:
         if y.shape != (self.B,) or y.dtype != torch.int64:
             raise ValueError("y must be int64 [B]")
 
-    def label_stats(self, y, den_scale_hook=None, ws=None):
-        ws = self.ws if ws is None else ws
+    def label_stats(self, y, den_scale_hook=None, max_ctas=0):
         L.call("osb_label_stats", L.ptr(y), L.ptr(self.class_w), self.B, self.C, self.variant, self.ignore_index,
-               L.ptr(self.den), L.ptr(self.label_counts), L.ptr(ws), ws.numel(), L.stream_ptr(self.dev))
+               L.ptr(self.den), L.ptr(self.label_counts), L.ptr(self.ws_label), self.ws_label.numel(), int(max_ctas),
+               L.stream_ptr(self.dev))
         if den_scale_hook is not None:
             den_scale_hook(self.den)
 
-    def forward(self, x, w, y, bias=None, write_dz=True, want_pred=True, den=None):
+    def forward(self, x, w, y, bias=None, write_dz=True, want_pred=True, den="step", flags=0, max_ctas=0):
+        """``den``: device double the loss is divided by ("step": this plan's own, None: ``loss`` = the numerator)."""
+        if isinstance(den, str):
+            den = self.den_step
         L.call("osb_head_forward", L.ptr(x), self.K, L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(self.class_w),
                self.B, self.K, self.C, self.variant, self.unk_weight, self.ignore_index,
-               L.ptr(self.den if den is None else den), self.valid_cols,
+               L.ptr(den), self.valid_cols,
                L.ptr(self.loss_num), L.ptr(self.loss), L.ptr(self.p_target), L.ptr(self.p_max),
                L.ptr(self.p_max_all) if want_pred else None, L.ptr(self.pred) if want_pred else None,
-               L.ptr(self.dz) if write_dz else None, self.lddz,
+               L.ptr(self.dz) if write_dz else None, self.lddz, self.planes, int(flags), int(max_ctas),
                L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def backward_dx(self, x, w, gscale=None):
-        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C,
-               L.ptr(gscale), L.ptr(self.dx), self.K, None, None, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+    def _dx_code(self):
+        return L.F32 if self.dx_dtype == torch.float32 else L.BF16
 
-    def backward_dw(self, x, w, gscale=None):
-        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C,
-               L.ptr(gscale), None, self.K, L.ptr(self.dw), L.ptr(self.db), L.ptr(self.ws), self.ws.numel(),
-               L.stream_ptr(self.dev))
+    def backward_dx(self, x, w, gscale=None, den=None, max_ctas=0):
+        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, self.planes, L.ptr(self.den_step if den is None else den),
+               L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), L.ptr(self.dx), self.K, self._dx_code(),
+               None, None, int(max_ctas), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+
+    def backward_dw(self, x, w, gscale=None, den=None):
+        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, self.planes, L.ptr(self.den_step if den is None else den),
+               L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), None, self.K, self._dx_code(),
+               L.ptr(self.dw), L.ptr(self.db), 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+
+    def backward_dw_partials(self, x):
+        """Only the dW GEMM: un-scaled split-K partials stay in the workspace (input of the peer-memory all-reduce);
+        with a bias the un-scaled column sums of dZ go to the db slots of the packed buffer."""
+        L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, self.planes, L.ptr(x), self.K, self.B, self.K, self.C,
+               L.ptr(self.db), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
     def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None):
         """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five
@@ -114,8 +154,8 @@ class HeadPlan:
         # dZ, so they become parallel branches of the graph.  Large batches fill the GPU with either kernel and stay serial.
         fork = self.B <= 4096 if parallel_backward is None else bool(parallel_backward)
         branch = torch.cuda.Stream(device=self.dev) if fork else None
-        # Entropic loss: the forward kernel takes the constant denominator and the label statistics (counts for the
-        # caller, the same denominator) become a branch beside the backward kernels instead of the first link of the chain.
+        # Entropic loss: the denominator is a constant, so the label statistics (counts for the caller) are a branch
+        # beside the backward kernels instead of the first link of the chain.
         side_labels = self.variant == L.ENTROPIC
         lbranch = torch.cuda.Stream(device=self.dev) if side_labels else None
 
@@ -124,25 +164,16 @@ class HeadPlan:
             # SMs nobody else wants, whichever kernel the hardware places first
             lbranch.wait_stream(side)
             with torch.cuda.stream(lbranch):
-                lib = L.load()
-                lib.osb_set_cta_limit(8)
-                try:
-                    self.label_stats(y, ws=self.ws_label)
-                finally:
-                    lib.osb_set_cta_limit(0)
+                self.label_stats(y, max_ctas=8)
 
         def body():
             if not side_labels:
-                # the forward kernel may start under the label statistics it follows (osb_head_forward_after_labels)
+                # the forward kernel runs under the label statistics it follows and waits for them only before it
+                # divides the loss (OSB_FWD_DEN_FROM_PREV_KERNEL); the grad-logits do not depend on the denominator
                 self.label_stats(y)
-                lib = L.load()
-                lib.osb_head_forward_after_labels(1)
-                try:
-                    self.forward(x, w, y, bias, want_pred=False)
-                finally:
-                    lib.osb_head_forward_after_labels(0)
+                self.forward(x, w, y, bias, want_pred=False, flags=L.FWD_DEN_FROM_PREV_KERNEL)
             else:
-                self.forward(x, w, y, bias, want_pred=False, den=self.den_const)
+                self.forward(x, w, y, bias, want_pred=False)
             if fork:
                 if side_labels:
                     labels_beside()
@@ -173,11 +204,6 @@ class HeadPlan:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         return graph
 
-    def backward_dw_partials(self, x):
-        """Only the dW GEMM: split-K partials stay in the workspace (input of the peer-memory all-reduce)."""
-        L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, L.ptr(x), self.K, self.B, self.K, self.C,
-               L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
-
     def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False, want_pred=False):
         """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches.  A training step
         has no use for the per-row arg-max / max probability (the reference's train loop reads the loss only,
@@ -185,9 +211,10 @@ class HeadPlan:
         if check:
             self._check(x, w, y)
         self.label_stats(y, den_scale_hook)
-        self.forward(x, w, y, bias, want_pred=want_pred)
-        self.backward_dx(x, w, gscale)
-        self.backward_dw(x, w, gscale)
+        den = self.den if den_scale_hook is not None else None
+        self.forward(x, w, y, bias, want_pred=want_pred, den="step" if den is None else den)
+        self.backward_dx(x, w, gscale, den=den)
+        self.backward_dw(x, w, gscale, den=den)
 
 
 class OscrPlan:

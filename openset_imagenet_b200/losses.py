@@ -59,7 +59,7 @@ class _LossFn(torch.autograd.Function):
             den = torch.empty(1, dtype=torch.float64, device=dev)
             counts = torch.empty(4, dtype=torch.int64, device=dev)
             L.call("osb_label_stats", L.ptr(y), L.ptr(cfg.class_w), B, Cc, cfg.variant, cfg.ignore_index,
-                   L.ptr(den), L.ptr(counts), L.ptr(ws), ws.numel(), st)
+                   L.ptr(den), L.ptr(counts), L.ptr(ws), ws.numel(), 0, st)
             if cfg.den_hook is not None:          # batch-sharded training: all-reduce the denominator
                 den = cfg.den_hook(den)
             out = torch.empty(1, dtype=torch.float32, device=dev)

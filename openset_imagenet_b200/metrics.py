@@ -60,10 +60,16 @@ def confidence(scores, target_labels, offset=0., unknown_class=-1, last_valid_cl
     if scores.shape[0] == 0:
         raise AttributeError("'int' object has no attribute 'item'")      # what sum([]).item() raises there
     sums, counts = confidence_sums(scores, target_labels, offset, unknown_class, last_valid_class)
+    return finish_confidence(sums, counts, scores.shape[1])
+
+
+def finish_confidence(sums: torch.Tensor, counts: torch.Tensor, num_classes: int):
+    """(sums [2] f64, counts [3] i64) -> the reference's ``(kn_conf, kn_count, neg_conf, neg_count)`` with its
+    empty-group rule (metrics.py:29-40).  The one host sync of the call."""
     s = sums.tolist()
-    kn_count, neg_count, bad = counts.tolist()
+    kn_count, neg_count, bad = (int(v) for v in counts.tolist())
     if bad:
-        raise IndexError(f"{bad} known label(s) out of range for {scores.shape[1]} classes")
+        raise IndexError(f"{bad} known label(s) out of range for {num_classes} classes")
     kn_conf = s[0] / kn_count if kn_count else 0.0
     neg_conf = s[1] / neg_count if neg_count else 0.0
     return kn_conf, kn_count, neg_conf, neg_count
@@ -104,8 +110,9 @@ class StreamingConfidence:
 
     def result(self):
         """``(kn_conf, kn_count, neg_conf, neg_count)`` with the reference's types and empty-group rule."""
-        s = self.sums.tolist()
-        kn_count, neg_count, bad = self.counts.tolist()
-        if bad:
-            raise IndexError(f"{bad} known label(s) out of range for {self.C} classes")
-        return (s[0] / kn_count if kn_count else 0.0), kn_count, (s[1] / neg_count if neg_count else 0.0), neg_count
+        return finish_confidence(self.sums, self.counts, self.C)
+
+    def result_sharded(self, group=None):
+        """``result()`` of a validation set whose batches were sharded over the ranks (one small all-reduce)."""
+        from .dist import allreduce_confidence
+        return finish_confidence(*allreduce_confidence(self.sums, self.counts, group), self.C)

@@ -93,6 +93,14 @@ def validate(model, data_loader, loss_fn, n_classes, trackers, cfg):
         loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         seen = 0
         if fused:
+            # the head reduces p_max over its own `valid_cols` columns: they must be the slice the reference's
+            # confidence() would take for this loss type (metrics.py:39, train.py:156-163)
+            want_cols = len(range(n_classes)[slice(None, last_valid_class)])
+            head = model.logits
+            if head.out_features != n_classes or head.valid_cols != want_cols:
+                raise ValueError(f"validate(): the fused head reduces the confidence maximum over {head.valid_cols} of "
+                                 f"{head.out_features} columns, but loss type {cfg.loss.type!r} with {n_classes} classes needs "
+                                 f"{want_cols} (build the head with last_valid_class={last_valid_class!r})")
             conf = StreamingConfidence(n_classes, offset, unknown_class, device=dev)
         else:
             data_len = len(data_loader.dataset)

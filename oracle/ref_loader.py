@@ -1,11 +1,12 @@
-"""Load the reference's hot-path files UNMODIFIED from /root/reference (build container only).
+"""Load the reference's hot-path files UNMODIFIED, from /root/reference (build container) or from the verbatim
+copies ``oracle/vendor_ref.py`` placed under ``oracle/_ref/`` (git-ignored; what travels to the GPU box).
 
 TEST INFRASTRUCTURE.  ``import openset_imagenet`` fails here (``robustness``, ``vast`` and
-``matplotlib`` are absent), but the three files on the path load by file path
+``matplotlib`` are absent), but the files on the path load by file path
 once ``vast.tools`` (device placement only, no arithmetic) and ``matplotlib`` (module-level
-imports only) are stubbed.  /root/reference does not exist on the GPU box: ``available()``
-is False there and everything that needs the reference is skipped; the golden vectors made
-from it (``oracle/make_golden.py`` -> ``tests/golden/``) are what travels.
+imports only) are stubbed.  Where neither location exists ``available()`` is False and everything that
+needs the reference is skipped; the golden vectors made from it (``oracle/make_golden.py`` ->
+``tests/golden/``) always travel.
 """
 from __future__ import annotations
 
@@ -15,12 +16,27 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("OSB_REFERENCE_ROOT", "/root/reference")
-_PKG = os.path.join(REF_ROOT, "openset_imagenet")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _cache: dict[str, types.ModuleType] = {}
 
 
+def package_dir() -> str | None:
+    """Directory holding the reference's losses.py / metrics.py / util.py / model.py, or None."""
+    for root in (REF_ROOT, _VENDORED):
+        pkg = os.path.join(root, "openset_imagenet")
+        if os.path.isfile(os.path.join(pkg, "losses.py")):
+            return pkg
+    return None
+
+
 def available() -> bool:
-    return os.path.isfile(os.path.join(_PKG, "losses.py"))
+    return package_dir() is not None
+
+
+def source() -> str:
+    """'checkout' (/root/reference), 'vendored' (oracle/_ref) or 'absent'."""
+    pkg = package_dir()
+    return "absent" if pkg is None else ("vendored" if pkg.startswith(_VENDORED) else "checkout")
 
 
 def _install_stubs() -> None:
@@ -67,10 +83,11 @@ def load(name: str) -> types.ModuleType:
     """name in {'losses', 'metrics', 'util', 'model'} -> the reference module object."""
     if name in _cache:
         return _cache[name]
-    if not available():
-        raise RuntimeError(f"reference not present at {REF_ROOT}")
+    pkg = package_dir()
+    if pkg is None:
+        raise RuntimeError(f"reference not present at {REF_ROOT} nor vendored under {_VENDORED} (python -m oracle.vendor_ref)")
     _install_stubs()
-    spec = importlib.util.spec_from_file_location(f"_osb_ref_{name}", os.path.join(_PKG, f"{name}.py"))
+    spec = importlib.util.spec_from_file_location(f"_osb_ref_{name}", os.path.join(pkg, f"{name}.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     _cache[name] = mod

@@ -1,16 +1,17 @@
 """GPU parity of the fused tcgen05 head against the float64 oracle on bf16-rounded inputs.
 
-Tolerances (north star: 1e-3 relative, bf16 in / fp32 accumulate):
-  * loss and per-row probabilities: 1e-3 (measured ~1e-6: the logits never leave fp32);
-  * dW, db: the grad-logits dZ is a bf16 tensor-core OPERAND ("bf16 in"), so dW = dZ^T X carries one bf16
-    rounding of dZ: 2^-9/sqrt(3) = 1.1e-3 RMS per element, measured 1.1e-3..2.0e-3 norm-wise against the
-    float64 oracle.  tcgen05 kind::f16 rejects mixed fp16 x bf16 operands (probed: illegal instruction), so
-    a wider dZ is not available at bf16 throughput.  The reference's own bf16 autocast path rounds dZ the
-    same way and additionally rounds the logits and dW to bf16; test_head_vs_torch_autocast checks that
-    this path is at least as close to the float64 result as that one.  Gate: 2.5e-3.
-  * dX is stored in bf16 (the dtype of the autocast backbone it feeds): one more bf16 rounding, gate 4e-3.
+Tolerances (north star: 1e-3 relative, bf16 in / fp32 accumulate) -- every gate below is 1e-3 norm-wise:
+  * loss and per-row probabilities: measured ~1e-6 (the logits never leave fp32);
+  * gradients, precision 'exact' (the default for heads of up to 256 classes and whenever a bias gradient is wanted):
+    the grad-logits reach the backward GEMMs as a bf16 pair (value + rounding residual, K-concatenated), dW / db / dX
+    accumulate in fp32: measured ~1e-5;
+  * gradients, precision 'fast' (one bf16 plane; what 'auto' picks for wide heads without a bias, e.g. the 1000-class
+    stress configuration): tcgen05 kind::f16 rejects mixed fp16 x bf16 operands (probed: illegal instruction), so dZ
+    carries one bf16 rounding: measured 6e-4..1e-3 norm-wise in dW and in an fp32 dX;
+  * a bf16 dX (bf16 features in -> bf16 gradient out, as an autocast backbone wants it) additionally carries the rounding
+    of its own storage format, ~1.6e-3 norm-wise whatever computed it; it is compared after rounding the oracle to bf16;
   * arg-max exact up to float32 near-ties."""
-DW_TOL = 2.5e-3
+TOL = 1e-3
 import numpy as np
 import pytest
 import torch
@@ -44,17 +45,23 @@ def _case(B, K, C, variant, seed, bias):
     return x, W, b, y, cw
 
 
-def _run(B, K, C, variant, bias, seed=0, unk_weight=1.0):
+def _bf16_dx_err(dx_bf16, ref_dx):
+    """A bf16 dX against the oracle rounded to the same storage format (see the module docstring)."""
+    return _rel(dx_bf16.float().cpu().numpy(), O.bf16_round(ref_dx.astype(np.float32)))
+
+
+def _run(B, K, C, variant, bias, seed=0, unk_weight=1.0, precision="auto", x_dtype=torch.float32):
+    """Features are bf16-representable either way; float32 features get the fp32 dX accumulator back, bf16 ones a bf16 dX."""
     from openset_imagenet_b200.model import FusedOpenSetHead
     x, W, b, y, cw = _case(B, K, C, variant, seed, bias)
     head = FusedOpenSetHead(K, C, bias=bias, variant=variant, unk_weight=unk_weight,
                             class_weights=None if cw is None else torch.tensor(cw, device=DEV),
-                            last_valid_class=-1 if variant == "garbage" else None, device=DEV)
+                            precision=precision, device=DEV)
     with torch.no_grad():
         head.weight.copy_(torch.tensor(W))
         if bias:
             head.bias.copy_(torch.tensor(b))
-    xt = torch.tensor(x, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    xt = torch.tensor(x, device=DEV, dtype=x_dtype, requires_grad=True)
     loss = head.loss(xt, torch.tensor(y, device=DEV))
     loss.backward()
     torch.cuda.synchronize()
@@ -74,9 +81,9 @@ SHAPES = [(64, 2048, 116), (256, 2048, 116), (1024, 2048, 152), (300, 128, 40), 
 @pytest.mark.parametrize("variant", ["entropic", "garbage"])
 def test_head_fwd_bwd_vs_oracle(B, K, C, variant):
     head, loss, xt, ref, (x, W, b, y) = _run(B, K, C, variant, bias=False, seed=B + C)
-    assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
-    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
-    assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+    assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+    assert _rel(xt.grad.cpu().numpy(), ref["dx"]) < TOL
     vc = C - 1 if variant == "garbage" else C
     pt, pm, pred = O.row_stats(ref["logits"], y, vc)
     st = head.last_stats
@@ -90,20 +97,23 @@ def test_head_fwd_bwd_vs_oracle(B, K, C, variant):
     assert np.mean(got == pred) > 0.999
 
 
-@pytest.mark.parametrize("B,K,C", [(256, 2048, 116), (1024, 2048, 152), (257, 512, 513), (384, 256, 1000)])
-def test_head_single_cta_kernels_vs_oracle(B, K, C):
-    """The single-CTA (cta_group::1) GEMM kernels stay in the library as the A/B reference of the CTA-pair kernels
-    (developer switch osb_debug_set_head_pairs); they must match the oracle too."""
-    from openset_imagenet_b200 import _lib as L
-    L.load().osb_debug_set_head_pairs(0)
-    try:
-        head, loss, xt, ref, _ = _run(B, K, C, "entropic", bias=True, seed=B + C + 1)
-    finally:
-        L.load().osb_debug_set_head_pairs(1)
-    assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
-    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
-    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < DW_TOL
-    assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+@pytest.mark.parametrize("B,K,C,variant,bias", [(256, 2048, 116, "entropic", True), (1024, 2048, 152, "garbage", False),
+                                                  (257, 512, 513, "entropic", False), (384, 256, 1000, "softmax", True),
+                                                  (1500, 1024, 256, "entropic", False), (5003, 192, 601, "garbage", False)])
+@pytest.mark.parametrize("precision", ["fast", "exact"])
+def test_head_precision_modes_and_bf16_dx(B, K, C, variant, bias, precision):
+    """Both grad-logits precisions against the oracle, with bf16 features (bf16 dX out).  'exact' meets 1e-3 on every
+    gradient; 'fast' meets it on dW and dX, while its db (column sums of the rounded grad-logits, heavy cancellation) is
+    only held to 1e-2 -- which is why 'auto' never picks 'fast' when a bias gradient is wanted."""
+    head, loss, xt, ref, _ = _run(B, K, C, variant, bias=bias, seed=B + C + 1, precision=precision, x_dtype=torch.bfloat16)
+    assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+    e_dw = _rel(head.weight.grad.cpu().numpy(), ref["dw"])
+    e_dx = _bf16_dx_err(xt.grad, ref["dx"])
+    print(f"B={B} K={K} C={C} {variant} {precision}: dW {e_dw:.2e}  bf16 dX vs bf16(oracle) {e_dx:.2e}")
+    assert e_dw < (TOL if precision == "exact" else 1.5e-3)
+    assert e_dx < (TOL if precision == "exact" else 2e-3)
+    if bias:
+        assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < (TOL if precision == "exact" else 1e-2)
 
 
 @pytest.mark.parametrize("B,K,C", [(64, 2048, 116), (1024, 2048, 152), (777, 1024, 190)])
@@ -120,10 +130,10 @@ def test_head_small_batch_splitk_vs_persistent_forward(B, K, C, variant):
             head, loss, xt, ref, (x, W, b, y) = _run(B, K, C, variant, bias=True, seed=B + C + 3)
         finally:
             L.load().osb_debug_set_head_splitk(1)
-        assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
-        assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
-        assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < 8e-3
-        assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+        assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+        assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+        assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < TOL
+        assert _rel(xt.grad.cpu().numpy(), ref["dx"]) < TOL
         vc = C - 1 if variant == "garbage" else C
         pt, pm, pred = O.row_stats(ref["logits"], y, vc)
         st = head.last_stats
@@ -133,7 +143,7 @@ def test_head_small_batch_splitk_vs_persistent_forward(B, K, C, variant):
         out[on] = (float(loss), st.p_target.cpu().numpy(), xt.grad.float().cpu().numpy())
     assert out[1][0] == pytest.approx(out[0][0], rel=1e-5)
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-4, atol=1e-7)
-    assert _rel(out[1][2], out[0][2]) < 6e-3      # two bf16 roundings of dZ and dX apart
+    assert _rel(out[1][2], out[0][2]) < 1e-4      # fp32 accumulations in different orders
 
 
 def test_head_many_tiles_per_cta_pair():
@@ -142,9 +152,9 @@ def test_head_many_tiles_per_cta_pair():
     B, K, C = 6000, 256, 1000
     for seed in (1, 2, 3):
         head, loss, xt, ref, _ = _run(B, K, C, "entropic", bias=False, seed=seed)
-        assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
-        assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
-        assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+        assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+        assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+        assert _rel(xt.grad.cpu().numpy(), ref["dx"]) < TOL
 
 
 def test_head_many_tiles_garbage_variant_with_bias():
@@ -152,12 +162,10 @@ def test_head_many_tiles_garbage_variant_with_bias():
     256-row tile (row clipping of the TMA stores, the valid-column maximum across column slices)."""
     B, K, C = 5003, 192, 601
     head, loss, xt, ref, (x, W, b, y) = _run(B, K, C, "garbage", bias=True, seed=7)
-    assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
-    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
-    # db sums 5003 bf16-rounded grad-logits per class with heavy cancellation (|db| << sum |dz|): the bf16 rounding of dZ
-    # (2^-9 per element, random sign) shows up relative to the much smaller sum -- measured 3.1e-3
-    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < 8e-3
-    assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+    assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < TOL       # a bias gradient makes 'auto' exact
+    assert _rel(xt.grad.cpu().numpy(), ref["dx"]) < TOL
     pt, pm, pred = O.row_stats(ref["logits"], y, C - 1)
     st = head.last_stats
     np.testing.assert_allclose(st.p_target.cpu().numpy(), pt, rtol=2e-3, atol=1e-6)
@@ -204,10 +212,10 @@ def test_head_plan_graph_replay_matches_eager_step(B, K, C, variant):
 @pytest.mark.parametrize("B,K,C", [(256, 2048, 116), (200, 256, 300), (384, 256, 1000)])
 def test_head_softmax_variant_and_bias(B, K, C):
     head, loss, xt, ref, _ = _run(B, K, C, "softmax", bias=True, seed=3)
-    assert float(loss) == pytest.approx(ref["loss"], rel=1e-3)
-    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < DW_TOL
-    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < DW_TOL
-    assert _rel(xt.grad.float().cpu().numpy(), ref["dx"]) < 4e-3
+    assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < TOL
+    assert _rel(xt.grad.cpu().numpy(), ref["dx"]) < TOL
 
 
 def test_head_unk_weight_and_upstream_scale():
@@ -216,11 +224,11 @@ def test_head_unk_weight_and_upstream_scale():
     head = FusedOpenSetHead(256, 116, variant="entropic", unk_weight=0.5, device=DEV)
     with torch.no_grad():
         head.weight.copy_(torch.tensor(W))
-    xt = torch.tensor(x, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    xt = torch.tensor(x, device=DEV, requires_grad=True)
     (3.0 * head.loss(xt, torch.tensor(y, device=DEV))).backward()
     ref = O.head_fwd_bwd(x, W, None, y, O.ENTROPIC, unk_weight=0.5)
-    assert _rel(head.weight.grad.cpu().numpy(), 3.0 * ref["dw"]) < DW_TOL
-    assert _rel(xt.grad.float().cpu().numpy(), 3.0 * ref["dx"]) < 4e-3
+    assert _rel(head.weight.grad.cpu().numpy(), 3.0 * ref["dw"]) < TOL
+    assert _rel(xt.grad.cpu().numpy(), 3.0 * ref["dx"]) < TOL
 
 
 def test_head_matches_reference_golden(golden):
@@ -235,10 +243,18 @@ def test_head_matches_reference_golden(golden):
     xt = torch.tensor(x, device=DEV, dtype=torch.float32, requires_grad=True)
     loss = head.loss(xt, torch.tensor(y, device=DEV))
     loss.backward()
-    assert float(loss) == pytest.approx(float(g["head_loss"]), rel=1e-3)
-    assert _rel(head.weight.grad.cpu().numpy(), g["head_dw"]) < DW_TOL
-    assert _rel(head.bias.grad.cpu().numpy(), g["head_db"]) < DW_TOL
-    assert _rel(xt.grad.cpu().numpy(), g["head_dx"]) < 4e-3
+    # the golden run is the reference in float64 on UN-rounded float32 inputs: what is left here is the bf16 rounding of
+    # the operands themselves ("bf16 in"), not of anything this path computes
+    assert float(loss) == pytest.approx(float(g["head_loss"]), rel=2e-3)
+    assert _rel(head.weight.grad.cpu().numpy(), g["head_dw"]) < 5e-3
+    assert _rel(head.bias.grad.cpu().numpy(), g["head_db"]) < 5e-3
+    assert _rel(xt.grad.cpu().numpy(), g["head_dx"]) < 5e-3
+    # ... and against the oracle on the operands as the kernels see them: 1e-3
+    ref = O.head_fwd_bwd(O.bf16_round(x), O.bf16_round(W), b, y, O.ENTROPIC)
+    assert float(loss) == pytest.approx(ref["loss"], rel=TOL)
+    assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+    assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < TOL
+    assert _rel(xt.grad.cpu().numpy(), ref["dx"]) < TOL
 
 
 def test_head_is_a_linear_layer_and_eval_mode():
@@ -260,9 +276,89 @@ def test_head_is_a_linear_layer_and_eval_mode():
     assert float(l1) == pytest.approx(ref, rel=1e-3)
 
 
-def test_head_full_size_linearity():
-    """cfg 5 shape per GPU (16384 x 2048 -> 1000): gradients are linear in the upstream scale and the
-    loss is invariant to a row permutation (size-independent properties; the oracle is too slow here)."""
+def _oracle_big(x, W, y, variant, cw=None):
+    """The float64 oracle at benchmark sizes: same closed forms, evaluated in row blocks (a dense [B, C] float64
+    intermediate per block) so that 16384 x 2048 -> 1000 takes seconds and a few hundred MB on the host."""
+    B, K = x.shape
+    C = W.shape[0]
+    _, _, den = O.row_terms(variant, y, C, 1.0, cw)
+    Wd = W.astype(np.float64)
+    dw = np.zeros((C, K))
+    dx = np.empty((B, K))
+    num = 0.0
+    pt = np.empty(B)
+    pm = np.empty(B)
+    vc = C - 1 if variant == O.GARBAGE else C
+    for r0 in range(0, B, 2048):
+        r1 = min(B, r0 + 2048)
+        ref = O.head_fwd_bwd(x[r0:r1], W, None, y[r0:r1], variant, class_weights=cw, den=den)
+        dw += ref["dz"].T @ x[r0:r1].astype(np.float64)
+        dx[r0:r1] = ref["dz"] @ Wd
+        num += ref["num"]
+        pt[r0:r1], pm[r0:r1], _ = O.row_stats(ref["logits"], y[r0:r1], vc)
+    return dict(loss=num / den, dw=dw, dx=dx, p_target=pt, p_max=pm, den=den)
+
+
+def _plan_case(B, K, C, variant, seed, precision, dx_dtype):
+    from openset_imagenet_b200.functional import HeadPlan
+    dev = torch.device(DEV)
+    rng = np.random.default_rng(seed)
+    x = O.bf16_round(rng.standard_normal((B, K)).astype(np.float32))
+    W = O.bf16_round((rng.standard_normal((C, K)) / np.sqrt(K)).astype(np.float32))
+    if variant == "garbage":
+        y = O.make_labels(B, C - 1, 1 / 3, seed=seed, neg_label=C - 1)
+        cw = O.class_weights_from_labels(np.concatenate([y, np.arange(C)]), C)
+        plan = HeadPlan(B, K, C, "garbage", class_weights=torch.tensor(cw, device=dev), last_valid_class=-1, device=dev,
+                        precision=precision, dx_dtype=dx_dtype)
+    else:
+        y = O.make_labels(B, C, 1 / 3, seed=seed)
+        cw = None
+        plan = HeadPlan(B, K, C, "entropic", device=dev, precision=precision, dx_dtype=dx_dtype)
+    xt = torch.tensor(x, device=dev, dtype=torch.bfloat16)
+    wt = torch.tensor(W, device=dev, dtype=torch.bfloat16)
+    yt = torch.tensor(y, device=dev)
+    return plan, (x, W, y, cw), (xt, wt, yt)
+
+
+@pytest.mark.parametrize("precision,dx_dtype", [("fast", torch.float32), ("fast", torch.bfloat16), ("exact", torch.float32)])
+def test_head_headline_shape_vs_oracle(precision, dx_dtype):
+    """BASELINE.json's large-head configuration as bench.py runs it (entropic, 16384 x 2048 -> 1000 per GPU, no bias,
+    HeadPlan.step) against the float64 oracle: loss, dW, dX, p_target, p_max.  'fast' is the benchmarked mode."""
+    plan, (x, W, y, cw), (xt, wt, yt) = _plan_case(16384, 2048, 1000, "entropic", 5, precision, dx_dtype)
+    plan.step(xt, wt, yt)
+    torch.cuda.synchronize()
+    ref = _oracle_big(x, W, y, O.ENTROPIC)
+    e_loss = abs(float(plan.loss) - ref["loss"]) / ref["loss"]
+    e_dw = _rel(plan.dw.cpu().numpy(), ref["dw"])
+    e_dx = _rel(plan.dx.cpu().numpy(), ref["dx"]) if dx_dtype == torch.float32 else _bf16_dx_err(plan.dx, ref["dx"])
+    print(f"headline {precision} dx={dx_dtype}: loss {e_loss:.2e} dW {e_dw:.2e} dX {e_dx:.2e}")
+    assert e_loss < TOL and e_dw < TOL
+    assert e_dx < (TOL if dx_dtype == torch.float32 else 2e-3)
+    np.testing.assert_allclose(plan.p_target.cpu().numpy(), ref["p_target"], rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(plan.p_max.cpu().numpy(), ref["p_max"], rtol=2e-3, atol=1e-7)
+    assert plan.label_counts.tolist() == [int((y >= 0).sum()), int((y < 0).sum()), 0, 0]
+
+
+def test_head_bg_protocol_shape_vs_oracle():
+    """BASELINE.json's garbage-class configuration (Protocol 3 shape, 151 + 1 classes, 1024 x 2048 per GPU, bias off as in
+    train.py:350-352), as bench.py --workload bg runs it: split-K forward, CUDA-graph replay."""
+    plan, (x, W, y, cw), (xt, wt, yt) = _plan_case(1024, 2048, 152, "garbage", 9, "auto", torch.bfloat16)
+    graph = plan.capture(xt, wt, yt)
+    graph.replay()
+    torch.cuda.synchronize()
+    ref = O.head_fwd_bwd(x, W, None, y, O.GARBAGE, class_weights=cw)
+    assert float(plan.loss) == pytest.approx(ref["loss"], rel=TOL)
+    assert _rel(plan.dw.cpu().numpy(), ref["dw"]) < TOL
+    assert _bf16_dx_err(plan.dx, ref["dx"]) < TOL
+    pt, pm, _ = O.row_stats(ref["logits"], y, 151)
+    np.testing.assert_allclose(plan.p_target.cpu().numpy(), pt, rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(plan.p_max.cpu().numpy(), pm, rtol=2e-3, atol=1e-7)
+    assert float(plan.den) == pytest.approx(ref["den"], rel=1e-12)
+
+
+def test_head_full_size_properties():
+    """cfg 5 shape per GPU through the autograd entry: gradients are linear in the upstream scale and the loss is
+    invariant to a row permutation (size-independent properties on top of the oracle test above)."""
     from openset_imagenet_b200.model import FusedOpenSetHead
     B, K, C = 16384, 2048, 1000
     g = torch.Generator(device=DEV).manual_seed(0)
@@ -280,22 +376,15 @@ def test_head_full_size_linearity():
     (2.0 * l2).backward()
     assert float(l1) == pytest.approx(float(l2), rel=1e-5)
     assert float(l1) > 0 and np.isfinite(float(l1))
-    assert _rel(head.weight.grad.cpu().numpy(), 2.0 * dw1.cpu().numpy()) < DW_TOL
-    assert _rel(x2.grad.float().cpu().numpy(), 2.0 * x1.grad[perm].float().cpu().numpy()) < 4e-3
-    # against cuBLAS + the row-wise loss kernel (an independent path through the same library)
-    import openset_imagenet_b200 as osb
-    x3 = x.clone().float().requires_grad_(True)
-    x3f = x3
-    l3 = osb.EntropicOpensetLoss(C, validate_labels=False)(torch.nn.functional.linear(x3f, head.weight.detach().bfloat16().float()), y)
-    l3.backward()
-    assert float(l1) == pytest.approx(float(l3), rel=1e-4)
-    assert _rel(x1.grad.float().cpu().numpy(), x3.grad.cpu().numpy()) < 4e-3
+    assert _rel(head.weight.grad.cpu().numpy(), 2.0 * dw1.cpu().numpy()) < 1e-5       # same products, another row order
+    assert torch.equal(x2.grad, (2.0 * x1.grad[perm].float()).bfloat16())             # rows are independent: bit-equal
 
 
 @pytest.mark.parametrize("B,K,C", [(256, 2048, 116), (1024, 2048, 152), (512, 512, 1000)])
 def test_head_vs_torch_autocast(B, K, C):
     """The reference path as PyTorch runs it in bf16 (nn.Linear under autocast -> reference-style soft-target
-    cross-entropy -> backward) against this path, both measured against the float64 oracle."""
+    cross-entropy -> backward) against this path, both measured against the float64 oracle: this path must meet 1e-3
+    and be at least as close as autocast (which rounds the logits, the grad-logits and dW to bf16)."""
     head, loss, xt, ref, (x, W, b, y) = _run(B, K, C, "entropic", bias=False, seed=11)
     lin = torch.nn.Linear(K, C, bias=False, device=DEV)
     with torch.no_grad():
@@ -312,15 +401,14 @@ def test_head_vs_torch_autocast(B, K, C):
     ref_loss.backward()
     e_ours_dw = _rel(head.weight.grad.cpu().numpy(), ref["dw"])
     e_ref_dw = _rel(lin.weight.grad.cpu().numpy(), ref["dw"])
-    e_ours_dx = _rel(xt.grad.float().cpu().numpy(), ref["dx"])
+    e_ours_dx = _rel(xt.grad.cpu().numpy(), ref["dx"])
     e_ref_dx = _rel(xr.grad.cpu().numpy(), ref["dx"])
     e_ours_loss = abs(float(loss) - ref["loss"]) / ref["loss"]
     e_ref_loss = abs(float(ref_loss) - ref["loss"]) / ref["loss"]
     print(f"B={B} K={K} C={C}: loss ours {e_ours_loss:.2e} torch-bf16 {e_ref_loss:.2e} | dW ours {e_ours_dw:.2e} "
           f"torch-bf16 {e_ref_dw:.2e} | dX ours {e_ours_dx:.2e} torch-bf16 {e_ref_dx:.2e}")
-    assert e_ours_loss <= max(1e-3, e_ref_loss)
-    assert e_ours_dw <= max(1e-3, 1.05 * e_ref_dw)
-    assert e_ours_dx <= max(1e-3, 1.05 * e_ref_dx) or e_ours_dx < 4e-3
+    assert e_ours_loss < TOL and e_ours_dw < TOL and e_ours_dx < TOL
+    assert e_ours_dw <= e_ref_dw and e_ours_dx <= e_ref_dx
 
 
 # ---- peer-memory all-reduce of dW (multi-GPU path), exercised on one GPU -----------------------------------------
@@ -332,37 +420,40 @@ def _partials_of(plan):
     return plan.ws[off:off + 4 * splits * n].view(torch.float32).view(splits, n).clone()
 
 
-def _run_plan(B, K, C, seed):
+def _run_plan(B, K, C, seed, bias=False):
     from openset_imagenet_b200.functional import HeadPlan
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(seed)
     x = torch.randn(B, K, device=dev, generator=g).bfloat16()
     w = (torch.randn(C, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    bv = torch.randn(C, device=dev, generator=g) if bias else None
     y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=seed), device=dev)
-    plan = HeadPlan(B, K, C, "entropic", device=dev)
+    plan = HeadPlan(B, K, C, "entropic", device=dev, bias=bias)
     plan.label_stats(y)
-    plan.forward(x, w, y)
+    plan.forward(x, w, y, bv, den=None)               # the loss slot holds this shard's numerator
     return plan, x, w, y
 
 
 def test_peer_allreduce_world_1_is_the_local_split_k_reduction():
     from openset_imagenet_b200 import _lib as L
     from openset_imagenet_b200.dist import PeerGradAllReduce
-    plan, x, w, y = _run_plan(2048, 512, 200, seed=3)
+    plan, x, w, y = _run_plan(2048, 512, 200, seed=3, bias=True)
+    num = plan.loss.clone()
     plan.backward_dw(x, w)
-    want = plan.dw.clone()
-    loss = plan.loss.clone()
+    want, want_db = plan.dw.clone(), plan.db.clone()
     plan.dw.zero_()
-    plan.backward_dw_partials(x)
+    plan.backward_dw_partials(x)                                  # un-scaled column sums of dZ land in the db slots
     flags = torch.zeros(L.size("osb_head_dw_allreduce_flag_bytes", 1) // 4, dtype=torch.int32, device="cuda")
-    ar = PeerGradAllReduce(plan, [plan.ws.data_ptr()], [plan.flat.data_ptr()], [flags.data_ptr()], 0, 1, n_extra=1)
-    for _ in range(3):                                           # epochs 1, 2, 3 on the same flags
+    ar = PeerGradAllReduce(plan, [plan.ws.data_ptr()], [plan.flat.data_ptr()], [flags.data_ptr()], 0, 1)
+    for _ in range(3):                                           # epochs 1, 2, 3: the counter lives in the flag area
         plan.dw.zero_()
-        torch.cuda.current_stream().wait_event(ar.run())
+        torch.cuda.current_stream().wait_event(ar.run(plan.den_step))
         torch.cuda.synchronize()
         assert torch.equal(plan.dw, want)
-        assert torch.equal(ar.extra_sum[:1], loss)
-    assert ar.error_word(flags) == 0
+        assert torch.equal(ar.extra_sum[:200], want_db)          # bias gradient: summed and scaled like dW
+        assert torch.equal(ar.extra_sum[200:], num)              # loss numerator: plain sum
+    assert ar.failed_epoch() == 0
+    assert int(flags[2 + 2]) == 3
 
 
 def test_peer_allreduce_two_emulated_ranks_sum_in_fixed_order():
@@ -382,28 +473,69 @@ def test_peer_allreduce_two_emulated_ranks_sum_in_fixed_order():
     for r in range(2):
         for s in range(parts[r].shape[0]):
             acc = acc + parts[r][s]                              # the kernel's order: rank 0 split 0, split 1, ..., rank 1 ...
-    losses = [p.loss.clone() for p in plans]
+    den = torch.full((1,), 2.0 * B, dtype=torch.float64, device="cuda")
+    acc = acc * (1.0 / (2.0 * B))                                # g / den with g = 1
+    nums = [p.loss.clone() for p in plans]
     nfl = L.size("osb_head_dw_allreduce_flag_bytes", 2) // 4
     flags = [torch.zeros(nfl, dtype=torch.int32, device="cuda") for _ in range(2)]
     ws_ptrs = [p.ws.data_ptr() for p in plans]
     flat_ptrs = [p.flat.data_ptr() for p in plans]
     flag_ptrs = [f.data_ptr() for f in flags]
+    ars = []
     for r in range(2):
         peer = 1 - r
         flags[r][peer] = 1                                       # "peer's partials are ready"
         flags[r][2 + peer] = 1                                   # "peer has published its slice"
-        ar = PeerGradAllReduce(plans[r], ws_ptrs, flat_ptrs, flag_ptrs, r, 2, n_extra=1)
-        torch.cuda.current_stream().wait_event(ar.run())
+        ar = PeerGradAllReduce(plans[r], ws_ptrs, flat_ptrs, flag_ptrs, r, 2)
+        torch.cuda.current_stream().wait_event(ar.run(den))
         torch.cuda.synchronize()
-        assert ar.error_word(flags[r]) == 0
-        assert torch.equal(ar.extra_sum[:1], losses[0] + losses[1])
+        assert ar.failed_epoch() == 0
+        assert torch.equal(ar.extra_sum[:1], nums[0] + nums[1])
+        ars.append(ar)
     for p in plans:                                              # both gradients complete and bit-identical
         assert torch.equal(p.dw.reshape(-1), acc)
-    # a rank whose peer never shows up gives up instead of hanging (stamps of epoch 2 are missing)
-    ar = PeerGradAllReduce(plans[0], ws_ptrs, flat_ptrs, flag_ptrs, 0, 2, n_extra=1)
-    ar.epoch = 1
+    # a rank whose peer never shows up gives up instead of hanging (the peer's stamps of epoch 2 are missing), stores
+    # NOTHING and poisons the summed loss
+    plans[0].dw.fill_(7.0)
     L.load().osb_debug_set_allreduce_timeout(20_000_000)         # ~10 ms
-    torch.cuda.current_stream().wait_event(ar.run())
+    try:
+        torch.cuda.current_stream().wait_event(ars[0].run(den))
+        torch.cuda.synchronize()
+    finally:
+        L.load().osb_debug_set_allreduce_timeout(0)
+    assert ars[0].failed_epoch() == 2
+    assert bool(torch.isnan(ars[0].extra_sum[0]))
+    assert bool((plans[0].dw == 7.0).all())
+    with pytest.raises(RuntimeError, match="gave up"):
+        ars[0].check()
+
+
+def test_peer_sum_world_1_and_emulated_pair():
+    """osb_peer_sum: the loss denominator's sum over the ranks through (32 bits, epoch) words in peer memory."""
+    from openset_imagenet_b200 import _lib as L
+    nb = L.size("osb_peer_sum_bytes", 2) // 4
+    slots = [torch.zeros(nb, dtype=torch.int32, device="cuda") for _ in range(2)]
+    vin = torch.tensor([3.25, -1e300, 2.0 ** -40], dtype=torch.float64, device="cuda")
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+    one = (L.C.c_void_p * 1)(slots[0].data_ptr())
+    for _ in range(3):                                           # epochs 1..3 alternate the two slot parities
+        L.call("osb_peer_sum", L.ptr(vin), L.ptr(out), 3, one, 0, 1, L.stream_ptr(torch.device("cuda")))
+        torch.cuda.synchronize()
+        assert torch.equal(out, vin)
+    # two emulated ranks: rank 1 runs first and times out waiting for rank 0 ... after leaving its words in rank 0's area
+    for t in slots:
+        t.zero_()
+    two = (L.C.c_void_p * 2)(slots[0].data_ptr(), slots[1].data_ptr())
+    v1 = torch.tensor([10.0], dtype=torch.float64, device="cuda")
+    v0 = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+    o = torch.zeros(1, dtype=torch.float64, device="cuda")
+    L.load().osb_debug_set_allreduce_timeout(20_000_000)
+    try:
+        L.call("osb_peer_sum", L.ptr(v1), L.ptr(o), 1, two, 1, 2, L.stream_ptr(torch.device("cuda")))
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(o[0]))                           # rank 0 never showed up
+    finally:
+        L.load().osb_debug_set_allreduce_timeout(0)
+    L.call("osb_peer_sum", L.ptr(v0), L.ptr(o), 1, two, 0, 2, L.stream_ptr(torch.device("cuda")))
     torch.cuda.synchronize()
-    L.load().osb_debug_set_allreduce_timeout(0)
-    assert ar.error_word(flags[0]) == 2
+    assert float(o[0]) == 10.5                                   # rank 0 finds rank 1's epoch-1 words waiting

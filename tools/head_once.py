@@ -12,7 +12,6 @@ x = torch.randn(B, K, device=dev).bfloat16()
 w = (torch.randn(C, K, device=dev) / K ** 0.5).bfloat16()
 y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=1), device=dev)
 from openset_imagenet_b200 import _lib as L
-if os.environ.get('OSB_PAIRS') == '0': L.load().osb_debug_set_head_pairs(0)
 plan = HeadPlan(B, K, C, device=dev)
 for _ in range(reps):
     out = plan.step(x, w, y)

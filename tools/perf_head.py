@@ -33,37 +33,33 @@ def head_case(B, K, C, variant="entropic"):
     w = head.weight.detach().bfloat16().contiguous()
     st = L.stream_ptr(dev)
     ws = torch.zeros(L.size("osb_head_workspace_bytes", B, K, C) + (1 << 20), dtype=torch.uint8, device=dev)
+    wsl = torch.zeros(L.size("osb_loss_workspace_bytes", B) + 256, dtype=torch.uint8, device=dev)
+    PLANES = int(os.environ.get("OSB_PLANES", "1"))
     den = torch.full((1,), float(B), dtype=torch.float64, device=dev)
     counts = torch.empty(4, dtype=torch.int64, device=dev)
     loss = torch.empty(1, device=dev); num = torch.empty(1, dtype=torch.float64, device=dev)
     stats = torch.empty(3, B, device=dev); pred = torch.empty(B, dtype=torch.int32, device=dev)
     _al = int(os.environ.get("OSB_LDDZ_ALIGN", "8")); lddz = (C + _al - 1) // _al * _al
-    dz = torch.empty(B, lddz, dtype=torch.bfloat16, device=dev)
+    dz = torch.empty(PLANES, B, lddz, dtype=torch.bfloat16, device=dev)
     dx = torch.empty(B, K, dtype=torch.bfloat16, device=dev); dw = torch.empty(C, K, device=dev)
     vnum = {"entropic": 0, "softmax": 1, "garbage": 2}[variant]
-    def lab(): L.call("osb_label_stats", y.data_ptr(), L.ptr(cw), B, C, vnum, -100, den.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), st)
+    def lab(): L.call("osb_label_stats", y.data_ptr(), L.ptr(cw), B, C, vnum, -100, den.data_ptr(), counts.data_ptr(), wsl.data_ptr(), wsl.numel(), 0, st)
     def fwd(): L.call("osb_head_forward", x.data_ptr(), K, w.data_ptr(), None, y.data_ptr(), L.ptr(cw), B, K, C, vnum, 1.0, -100, den.data_ptr(), C,
-                      num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), dz.data_ptr(), lddz, ws.data_ptr(), ws.numel(), st)
+                      num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), dz.data_ptr(), lddz, PLANES, 0, 0, ws.data_ptr(), ws.numel(), st)
     def fwd_nodz(): L.call("osb_head_forward", x.data_ptr(), K, w.data_ptr(), None, y.data_ptr(), L.ptr(cw), B, K, C, vnum, 1.0, -100, den.data_ptr(), C,
-                      num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), None, lddz, ws.data_ptr(), ws.numel(), st)
-    def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, None, None, ws.data_ptr(), ws.numel(), st)
-    def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, None, K, dw.data_ptr(), None, ws.data_ptr(), ws.numel(), st)
-    def bdwp(): L.call("osb_head_backward_dw_partials", dz.data_ptr(), lddz, x.data_ptr(), K, B, K, C, ws.data_ptr(), ws.numel(), st)
+                      num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), None, lddz, PLANES, 0, 0, ws.data_ptr(), ws.numel(), st)
+    def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, PLANES, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, L.BF16, None, None, 0, ws.data_ptr(), ws.numel(), st)
+    def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, PLANES, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, None, K, L.BF16, dw.data_ptr(), None, 0, ws.data_ptr(), ws.numel(), st)
+    def bdwp(): L.call("osb_head_backward_dw_partials", dz.data_ptr(), lddz, PLANES, x.data_ptr(), K, B, K, C, None, ws.data_ptr(), ws.numel(), st)
     def step(): lab(); fwd(); bdx(); bdw()
     fl = 2.0 * B * K * C
     print(f"--- head B={B} K={K} C={C} {variant}: GEMM flops each {fl/1e9:.2f} GF")
     lib = L.load()
     lib.osb_debug_set_head_dbg(int(os.environ.get('OSB_DBG', '0')))
-    def bdx1():
-        lib.osb_debug_set_head_pairs(0); bdx(); lib.osb_debug_set_head_pairs(1)
-    def bdw1():
-        lib.osb_debug_set_head_pairs(0); bdw(); lib.osb_debug_set_head_pairs(1)
-    def fwd1():
-        lib.osb_debug_set_head_pairs(0); fwd(); lib.osb_debug_set_head_pairs(1)
     def fwd_persist():
         lib.osb_debug_set_head_splitk(0); fwd(); lib.osb_debug_set_head_splitk(1)
-    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd persistent", fwd_persist, fl), ("fwd 1-CTA", fwd1, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl), ("dx 1-CTA", bdx1, fl),
-                        ("dw(K3+reduce)", bdw, fl), ("dw 1-CTA", bdw1, fl), ("dw GEMM only", bdwp, fl), ("step", step, 3 * fl)]:
+    for name, fn, f in [("label_stats", lab, 0), ("fwd(K1)", fwd, fl), ("fwd persistent", fwd_persist, fl), ("fwd no dz", fwd_nodz, fl), ("dx(K2)", bdx, fl),
+                        ("dw(K3+reduce)", bdw, fl), ("dw GEMM only", bdwp, fl), ("step", step, 3 * fl)]:
         med, mn = timeit(fn)
         med2, mn2 = timeit(fn, flush_l2=False)
         print(f"{name:16s} cold-L2 med {med:9.1f} us min {mn:9.1f} us | warm med {med2:9.1f} us" + (f" | {f/med/1e6:8.1f} TF/s cold, {f/med2/1e6:8.1f} warm" if f else ""))

@@ -11,12 +11,12 @@ x = torch.randn(B, K, device=dev).bfloat16()
 w = (torch.randn(C, K, device=dev) / K ** 0.5).bfloat16()
 dx = torch.empty(B, K, dtype=torch.bfloat16, device=dev)
 ws = torch.zeros(L.size("osb_head_workspace_bytes", B, K, C) + (1 << 20), dtype=torch.uint8, device=dev)
+den = torch.ones(1, dtype=torch.float64, device=dev)
 st = L.stream_ptr(dev)
 lib = L.load()
 lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
-def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, None, None, ws.data_ptr(), ws.numel(), st)
+def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, 1, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, L.BF16, None, None, int(os.environ.get("OSB_CTAS", "0")), ws.data_ptr(), ws.numel(), st)
 lib.osb_debug_set_head_dbg(int(os.environ.get('OSB_DBG', '0')))
-lib.osb_set_cta_limit(int(os.environ.get('OSB_CTAS', '0')))
 for _ in range(3): bdx()
 torch.cuda.synchronize()
 trace = torch.zeros(512, 64, dtype=torch.int64, device=dev)

@@ -14,7 +14,6 @@ plan = HeadPlan(B, K, C, device=dev)
 lib = L.load()
 lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
 trace = torch.zeros(512, 64, dtype=torch.int64, device=dev)
-if os.environ.get("OSB_PAIRS") == "0": lib.osb_debug_set_head_pairs(0)
 plan.label_stats(y)
 for _ in range(3): plan.forward(x, w, y)
 torch.cuda.synchronize()
