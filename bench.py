@@ -37,8 +37,8 @@ sys.path.insert(0, ROOT)
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
-HEAD = dict(B=16384, K=2048, C=1000, variant="entropic", neg_frac=1.0 / 3.0)
-BG = dict(B=1024, K=2048, C=152, variant="garbage", neg_frac=1.0 / 3.0)
+HEAD = dict(B=16384, K=2048, C=1000, variant="entropic", neg_frac=1.0 / 3.0, precision="fast")
+BG = dict(B=1024, K=2048, C=152, variant="garbage", neg_frac=1.0 / 3.0, precision="exact")
 OSCR = dict(N=1_000_000, C=116)
 METRIC = "EOS head fwd+bwd samples/s"
 
@@ -224,7 +224,7 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     nbuf = 3                                        # 3 x 64 MB of features + 64 MB dX + 32 MB dZ: far larger than the 126 MB L2
     xs, ys, ys_np, w, cw = make_head_inputs(cfg, dev, nbuf, seed=1234 + rank)
     plan_kw = dict(class_weights=cw, last_valid_class=-1 if cfg["variant"] == "garbage" else None, device=dev,
-                   precision=cfg.get("precision", "auto"))
+                   precision=cfg.get("precision", "exact"))
     allreduce = "none"
     if world > 1:
         try:            # dW all-reduce over NVLink peer memory, fused with the split-K reduction (no NCCL on the data path)

@@ -14,18 +14,18 @@ _VARIANTS = {"entropic": L.ENTROPIC, "softmax": L.SOFTMAX, "garbage": L.GARBAGE}
 _DEFAULT_IGNORE = {"entropic": -100, "softmax": -1, "garbage": -100}
 
 
-def resolve_planes(precision: str, C: int, bias: bool) -> int:
-    """dZ planes for a precision policy.  'exact' keeps the bf16 rounding residual of the grad-logits in a second plane
-    (gradients within ~1e-5 of float64 at twice the backward MMA count); 'fast' is a single bf16 plane (~1e-3 norm-wise
-    in dW / dX, more in db, whose column sums cancel); 'auto' is exact where it is free -- the launch-latency-bound
-    protocol heads (C <= 256) -- and wherever a bias gradient is wanted."""
+def resolve_planes(precision: str, C: int = 0, bias: bool = False) -> int:
+    """dZ planes for a precision mode.
+    'exact' (default): the bf16 rounding residual of the grad-logits travels in a second plane and the backward GEMMs
+        accumulate both in fp32 -- dW / db / dX within ~1e-5 of float64, at twice the backward MMA count (free for the
+        launch-latency-bound protocol heads, ~1.6x the step time of the 1000-class stress configuration);
+    'fast': one bf16 plane, i.e. plain bf16 tensor-core operands: 6e-4 .. 1.5e-3 norm-wise in dW / dX depending on the
+        shape (measured), more in db, whose column sums cancel.  The benchmarked mode of the large-head configuration."""
     if precision == "exact":
         return 2
     if precision == "fast":
         return 1
-    if precision == "auto":
-        return 2 if (C <= 256 or bias) else 1
-    raise ValueError(f"precision must be 'auto', 'fast' or 'exact', got {precision!r}")
+    raise ValueError(f"precision must be 'exact' or 'fast', got {precision!r}")
 
 
 class HeadPlan:
@@ -41,7 +41,7 @@ class HeadPlan:
     def __init__(self, B: int, K: int, C: int, variant: str = "entropic", unk_weight: float = 1.0,
                  class_weights: torch.Tensor | None = None, ignore_index: int | None = None,
                  last_valid_class=None, bias: bool = False, device=None, grad_buffer: torch.Tensor | None = None,
-                 workspace: torch.Tensor | None = None, precision: str = "auto", dx_dtype: torch.dtype = torch.bfloat16,
+                 workspace: torch.Tensor | None = None, precision: str = "exact", dx_dtype: torch.dtype = torch.bfloat16,
                  n_tail: int = 1):
         if K % 64 != 0:
             raise ValueError("HeadPlan needs in_features % 64 == 0 (FusedOpenSetHead pads other widths)")

@@ -153,9 +153,10 @@ class FusedOpenSetHead(nn.Linear):
             (train.py:156-163): -1 for 'garbage', None otherwise.
         validate_labels: read one counter back per call to raise the reference's IndexError for labels
             >= out_features (a host sync); off by default, bad labels then give a NaN loss.
-        precision: 'auto' | 'fast' | 'exact' (``functional.resolve_planes``): how the grad-logits reach the backward
-            GEMMs.  'exact' keeps their bf16 rounding residual in a second plane (gradients ~1e-5 from float64);
-            'fast' is one bf16 plane (~1e-3); 'auto' is exact for heads of up to 256 classes, where it is free.
+        precision: 'exact' (default) | 'fast' (``functional.resolve_planes``): how the grad-logits reach the backward
+            GEMMs.  'exact' keeps their bf16 rounding residual in a second plane (gradients ~1e-5 from float64, the
+            1e-3 contract holds for every shape); 'fast' is one bf16 plane (6e-4 .. 1.5e-3 norm-wise, half the
+            backward MMAs: worth it only for wide heads on large batches).
 
     The bf16 copy of the weights the kernels read is cached per weight VERSION (``Tensor._version``): every
     in-place update through the autograd-visible tensor (optimizers, ``copy_`` under ``no_grad``) refreshes it.
@@ -164,7 +165,7 @@ class FusedOpenSetHead(nn.Linear):
 
     def __init__(self, in_features, out_features, bias=False, variant="entropic", unk_weight=1.0,
                  class_weights=None, ignore_index=None, last_valid_class=_AUTO, validate_labels=False,
-                 precision="auto", device=None, dtype=None):
+                 precision="exact", device=None, dtype=None):
         super().__init__(in_features, out_features, bias=bias, device=device, dtype=dtype)
         if variant not in _VARIANTS:
             raise ValueError(f"unknown variant {variant!r}")
