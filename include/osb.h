@@ -153,6 +153,8 @@ int osb_head_forward_is_splitk(int64_t B, int K, int C);
  * osb_head_backward_dw_partials runs only the dW GEMM: `osb_head_dw_splits(B,K,C)` fp32 partial matrices [C,K]
  * (UN-scaled: sums of dz * x) are left at byte offset osb_head_dw_partials_offset() of the workspace, consecutive
  * splits C*K elements apart; db_partial (nullable) [C] float32 receives the un-scaled column sums of dz.
+ * local_reduce != 0 sums the splits into the first one on this GPU (pass splits = 1 to the all-reduce then): worth it
+ * when there are many splits (small batches), so that ONE matrix per rank crosses NVLink.
  * osb_head_dw_allreduce (one launch per rank): rank r sums slice r of ALL ranks' partials in a fixed order
  * (bit-identical result on every rank), scales by gscale[0] / den[0] and stores it into every rank's dW; `n_extra`
  * floats per rank are summed into extra_out: the first n_extra - n_plain of them (db) are scaled like dW, the last
@@ -167,7 +169,7 @@ int osb_head_forward_is_splitk(int64_t B, int K, int C);
 size_t osb_head_dw_partials_offset(void);
 int osb_head_dw_splits(int64_t B, int K, int C);
 int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
-                                  int64_t B, int K, int C, float* db_partial,
+                                  int64_t B, int K, int C, float* db_partial, int local_reduce,
                                   void* ws, size_t ws_bytes, void* stream);
 size_t osb_head_dw_allreduce_flag_bytes(int world);
 int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,

@@ -1079,10 +1079,10 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 
 // dW = g * sum_s partials[s]  (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
-dw_reduce_kernel(const float4* __restrict__ partials, int splits, size_t n4, const float* __restrict__ gscale,
-                 const double* __restrict__ den, float4* __restrict__ dw) {
+dw_reduce_kernel(const float4* partials, int splits, size_t n4, const float* __restrict__ gscale,
+                 const double* __restrict__ den, float4* dw) {
     pdl_wait();                 // the partials come from the dW GEMM in front of this kernel
-    const float gs = (float)((gscale ? (double)gscale[0] : 1.0) / den[0]);
+    const float gs = den ? (float)((gscale ? (double)gscale[0] : 1.0) / den[0]) : 1.f;      // den == NULL: plain sum
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 acc = partials[i];
         for (int s = 1; s < splits; ++s) {
@@ -1772,7 +1772,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
 extern "C" size_t osb_head_dw_partials_offset(void) { return kWsOffDw; }
 extern "C" int osb_head_dw_splits(int64_t B, int K, int C) { return dw_splits((int)B, K, C); }
 extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
-                                             int64_t B, int K, int C, float* db_partial,
+                                             int64_t B, int K, int C, float* db_partial, int local_reduce,
                                              void* ws, size_t ws_bytes, void* stream) {
     OSB_ENTRY_GUARD();
     int rc = check_backward_args("osb_head_backward_dw_partials", dz, lddz, dz_planes, x, ldx, B, K, C, ws, ws_bytes);
@@ -1781,6 +1781,19 @@ extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int d
     int splits = 1;
     rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits);
     if (rc) return rc;
+    if (local_reduce && splits > 1) {
+        // sum the splits into split 0 in place (every thread reads all splits of its elements before it writes them): the
+        // cross-GPU all-reduce then pulls ONE matrix per rank over NVLink instead of `splits`
+        float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsOffDw);
+        const size_t n4 = (size_t)C * K / 4;
+        int rgrid = (int)((n4 + 255) / 256);
+        const int cap = sm_count() * 8;
+        if (rgrid > cap) rgrid = cap;
+        cudaLaunchAttribute pdl_attr;
+        cudaLaunchConfig_t cfg = pdl_config(dim3(rgrid), dim3(256), 0, st, &pdl_attr);
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, dw_reduce_kernel, reinterpret_cast<const float4*>(partials), splits, n4,
+                                    (const float*)nullptr, (const double*)nullptr, reinterpret_cast<float4*>(partials)));
+    }
     if (db_partial) {
         db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, dz_planes, nullptr, nullptr, db_partial);
         OSB_LAUNCH_CHECK();

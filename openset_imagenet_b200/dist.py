@@ -115,7 +115,11 @@ class PeerGradAllReduce:
         self._extra = P(*[int(p) + 4 * n for p in flat_ptrs])
         self._flags = P(*[int(p) for p in flag_ptrs])
         self._flags_local = int(flag_ptrs[rank])
-        self.splits = L.size("osb_head_dw_splits", plan.B, plan.K, plan.C)
+        # many splits (small batches): they are summed on their own GPU first, ONE matrix per rank crosses NVLink; the two
+        # splits of a large batch are pulled as they are (the reduce is fused into the all-reduce, one pass less)
+        self.gemm_splits = L.size("osb_head_dw_splits", plan.B, plan.K, plan.C)
+        self.local_reduce = self.gemm_splits > 2
+        self.splits = 1 if self.local_reduce else self.gemm_splits
         self.n = n
         self.extra_sum = torch.zeros(max(self.n_extra, 1), dtype=torch.float32, device=plan.dev)
         self.stream = torch.cuda.Stream(device=plan.dev)
@@ -248,13 +252,17 @@ class ShardedHeadPlan:
             mark(0)
             p.forward(x, w, y, bias, want_pred=False, den=None)        # training step: no per-row predictions
             mark(1)
-            p.backward_dw_partials(x)
+            p.backward_dw_partials(x, local_reduce=self.peer.local_reduce)
             mark(2)
             self._abranch.wait_stream(cur)
             if not self.entropic:
                 self._abranch.wait_stream(self._lbranch)
                 cur.wait_stream(self._lbranch)
+            if marks is not None and len(marks) > 5:
+                marks[4].record(self._abranch)
             self.peer.launch(self.den_global, stream=self._abranch)
+            if marks is not None and len(marks) > 5:
+                marks[5].record(self._abranch)
             p.backward_dx(x, w, den=self.den_global, max_ctas=dx_ctas)
             mark(3)
             cur.wait_stream(self._abranch)

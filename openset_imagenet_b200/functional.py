@@ -137,11 +137,12 @@ class HeadPlan:
                L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), None, self.K, self._dx_code(),
                L.ptr(self.dw), L.ptr(self.db), 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def backward_dw_partials(self, x):
-        """Only the dW GEMM: un-scaled split-K partials stay in the workspace (input of the peer-memory all-reduce);
-        with a bias the un-scaled column sums of dZ go to the db slots of the packed buffer."""
+    def backward_dw_partials(self, x, local_reduce=False):
+        """Only the dW GEMM: un-scaled split-K partials stay in the workspace (input of the peer-memory all-reduce),
+        summed into the first one when ``local_reduce``; with a bias the un-scaled column sums of dZ go to the db slots
+        of the packed buffer."""
         L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, self.planes, L.ptr(x), self.K, self.B, self.K, self.C,
-               L.ptr(self.db), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+               L.ptr(self.db), 1 if local_reduce else 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
     def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None):
         """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five

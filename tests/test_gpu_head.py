@@ -443,10 +443,11 @@ def test_peer_allreduce_world_1_is_the_local_split_k_reduction():
     plan.backward_dw(x, w)
     want, want_db = plan.dw.clone(), plan.db.clone()
     plan.dw.zero_()
-    plan.backward_dw_partials(x)                                  # un-scaled column sums of dZ land in the db slots
     flags = torch.zeros(L.size("osb_head_dw_allreduce_flag_bytes", 1) // 4, dtype=torch.int32, device="cuda")
     ar = PeerGradAllReduce(plan, [plan.ws.data_ptr()], [plan.flat.data_ptr()], [flags.data_ptr()], 0, 1)
+    assert ar.local_reduce and ar.gemm_splits == 16              # many splits: summed locally, one matrix per rank is exchanged
     for _ in range(3):                                           # epochs 1, 2, 3: the counter lives in the flag area
+        plan.backward_dw_partials(x, local_reduce=ar.local_reduce)    # un-scaled column sums of dZ land in the db slots
         plan.dw.zero_()
         torch.cuda.current_stream().wait_event(ar.run(plan.den_step))
         torch.cuda.synchronize()
@@ -463,17 +464,22 @@ def test_peer_allreduce_two_emulated_ranks_sum_in_fixed_order():
     from openset_imagenet_b200 import _lib as L
     from openset_imagenet_b200.dist import PeerGradAllReduce
     B, K, C = 1024, 256, 136
-    plans = []
+    plans, xs_ = [], []
     for r in range(2):
         plan, x, w, y = _run_plan(B, K, C, seed=10 + r)
         plan.backward_dw_partials(x)
         plans.append(plan)
+        xs_.append(x)
     torch.cuda.synchronize()
     parts = [_partials_of(p) for p in plans]
     acc = torch.zeros(C * K, device="cuda")
+    for r in range(2):                                           # 16 splits: each rank sums its own first (split order) ...
+        loc = parts[r][0].clone()
+        for s in range(1, parts[r].shape[0]):
+            loc = loc + parts[r][s]
+        acc = acc + loc                                          # ... then the ranks are added in rank order
     for r in range(2):
-        for s in range(parts[r].shape[0]):
-            acc = acc + parts[r][s]                              # the kernel's order: rank 0 split 0, split 1, ..., rank 1 ...
+        plans[r].backward_dw_partials(xs_[r], local_reduce=True)
     den = torch.full((1,), 2.0 * B, dtype=torch.float64, device="cuda")
     acc = acc * (1.0 / (2.0 * B))                                # g / den with g = 1
     nums = [p.loss.clone() for p in plans]
