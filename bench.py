@@ -230,12 +230,15 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     allreduce = "none"
     if world > 1:
         try:            # dW all-reduce over NVLink peer memory, fused with the split-K reduction (no NCCL on the data path)
-            sp = ShardedHeadPlan(B, K, C, cfg["variant"], peer_allreduce=True, sm_reserve=args.sm_reserve, **plan_kw)
-            allreduce = "peer-memory kernel fused with the split-K reduction (osb_head_dw_allreduce), overlapped with dX"
+            sp = ShardedHeadPlan(B, K, C, cfg["variant"], peer_allreduce=True, sm_reserve=args.sm_reserve or None,
+                                 multicast=not args.no_multicast, **plan_kw)
+            allreduce = ("peer-memory kernel fused with the split-K reduction (osb_head_dw_allreduce), " +
+                         ("summed inside the NVSwitch (multimem.ld_reduce / multimem.st), " if sp.peer.mc_partials is not None else "peer loads, ") +
+                         "overlapped with dX")
         except Exception as e:                                  # no symmetric memory on this box: NCCL all-reduce
             if rank == 0:
                 print(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-            sp = ShardedHeadPlan(B, K, C, cfg["variant"], sm_reserve=args.sm_reserve, **plan_kw)
+            sp = ShardedHeadPlan(B, K, C, cfg["variant"], sm_reserve=args.sm_reserve or 32, **plan_kw)
             allreduce = "NCCL all-reduce of the packed fp32 [dW | loss] buffer, overlapped with dX"
     else:
         sp = ShardedHeadPlan(B, K, C, cfg["variant"], **plan_kw)
@@ -268,6 +271,10 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index) as clk:
+        if world > 1:
+            # the ranks leave the host barrier tens of microseconds apart: one more untimed step, whose all-reduce makes the
+            # GPUs meet, so that the K timed steps start aligned on the device
+            run_step(args.warmup)
         t0.record()
         for i in range(args.steps):
             run_step(i)
@@ -682,7 +689,9 @@ def main():
     ap.add_argument("--eager", action="store_true", help="launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-oscr", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the bg / resnet sub-objects of the default line")
-    ap.add_argument("--sm-reserve", type=int, default=16, help="SMs left to the gradient all-reduce while dX runs (N > 1)")
+    ap.add_argument("--sm-reserve", type=int, default=0, help="SMs left to the gradient all-reduce while dX runs (N > 1); "
+                    "0 = 8 with NVSwitch multicast, 16 with peer loads")
+    ap.add_argument("--no-multicast", action="store_true", help="all-reduce with peer loads instead of NVSwitch multimem (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()

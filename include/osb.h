@@ -165,6 +165,10 @@ int osb_head_forward_is_splitk(int64_t B, int K, int C);
  * and advances by one per launch, so the launch is CUDA-graph capturable and every replay is a new epoch; all ranks
  * must launch the same number of times.  A rank that waits ~2 s for a peer gives up: it stores nothing, sets every
  * plain extra to NaN and writes the epoch to the error word (osb_head_dw_allreduce_error reads it back, host sync).
+ * mc_partials / mc_dw (both or neither): MULTICAST addresses (NVSwitch, cuMulticast / torch symmetric memory's
+ * multicast_ptr) of the same partial and dW buffers.  With them the owner of a slice fetches the cross-rank sum with
+ * multimem.ld_reduce (added inside the switch: 1/world of the traffic) and broadcasts the result with multimem.st; the
+ * sum order is then the switch's (still one reduction per element, so all ranks stay bit-identical).
  * max_ctas bounds the grid (default 32) so the kernel overlaps dX. */
 size_t osb_head_dw_partials_offset(void);
 int osb_head_dw_splits(int64_t B, int K, int C);
@@ -175,7 +179,7 @@ size_t osb_head_dw_allreduce_flag_bytes(int world);
 int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,
                           void* const* peer_flags, int rank, int world, int splits, int64_t n, int64_t split_stride,
                           float* extra_out, int n_extra, int n_plain, const float* gscale, const double* den,
-                          int max_ctas, void* stream);
+                          const void* mc_partials /* nullable */, void* mc_dw /* nullable */, int max_ctas, void* stream);
 int osb_head_dw_allreduce_error(const void* flags_local, int world, uint32_t* epoch_out);   /* host sync; 0 = no failure */
 
 /* Sum of up to 8 doubles over the ranks through peer memory (the loss denominator of the softmax / garbage variants,

@@ -42,7 +42,7 @@ SIGNATURES = {
     "osb_head_dw_splits": (_i, [_i64, _i, _i]),
     "osb_head_backward_dw_partials": (_i, [_p, _i64, _i, _p, _i64, _i64, _i, _i, _p, _i, _p, _sz, _p]),
     "osb_head_dw_allreduce_flag_bytes": (_sz, [_i]),
-    "osb_head_dw_allreduce": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _i64, _p, _i, _i, _p, _p, _i, _p]),
+    "osb_head_dw_allreduce": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _i64, _p, _i, _i, _p, _p, _p, _p, _i, _p]),
     "osb_head_dw_allreduce_error": (_i, [_p, _i, _p]),
     "osb_peer_sum_bytes": (_sz, [_i]),
     "osb_peer_sum": (_i, [_p, _p, _i, _p, _i, _i, _p]),

@@ -26,6 +26,8 @@ struct ArParams {
     unsigned int* flags[kArMaxWorld];       // per rank: [0..W) ready stamps, [W..2W) done stamps, [2W] error word, [2W+1] exit
                                             // ticket, [2W+2] epochs completed so far (local)
     float* extra_out;                       // local [n_extra]
+    const float* mc_partials;               // nullable: MULTICAST address of the partial buffers (NVSwitch, multimem.ld_reduce)
+    float* mc_out;                          // nullable: multicast address of the dW buffers (multimem.st)
     const float* gscale;                    // nullable device scalar
     const double* den;                      // global loss denominator (device)
     long long n;                            // elements of dW (multiple of 4)
@@ -90,6 +92,39 @@ dw_allreduce_kernel(const ArParams p) {
         s_src[q] = reinterpret_cast<const float4*>(p.partials[q / p.splits]) + (long long)(q % p.splits) * stride4;
     __syncthreads();
     const long long tstride = (long long)gridDim.x * kArThreads;
+    if (p.mc_partials != nullptr) {
+        // NVSwitch path: ONE multimem.ld_reduce per element and split returns the sum over all ranks, added inside the switch
+        // (1 / world of the peer-load traffic and round trips); ONE multimem.st writes the result into every rank's dW.
+        // Each element is still reduced once, by its owner, so all ranks hold bit-identical gradients.
+        constexpr int kMc = 4;
+        const float4* mc_in = reinterpret_cast<const float4*>(p.mc_partials);
+        float4* mc_o = reinterpret_cast<float4*>(p.mc_out);
+        for (long long i0 = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; alive && i0 < hi; i0 += tstride * kMc) {
+            float4 acc[kMc];
+#pragma unroll
+            for (int e = 0; e < kMc; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < p.splits; ++sp) {
+                float4 v[kMc];
+#pragma unroll
+                for (int e = 0; e < kMc; ++e) {
+                    const long long i = i0 + e * tstride;
+                    v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < hi)
+                        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v[e].x), "=f"(v[e].y), "=f"(v[e].z), "=f"(v[e].w) : "l"(mc_in + (long long)sp * stride4 + i) : "memory");
+                }
+#pragma unroll
+                for (int e = 0; e < kMc; ++e) { acc[e].x += v[e].x; acc[e].y += v[e].y; acc[e].z += v[e].z; acc[e].w += v[e].w; }
+            }
+#pragma unroll
+            for (int e = 0; e < kMc; ++e) {
+                const long long i = i0 + e * tstride;
+                if (i < hi)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 :: "l"(mc_o + i), "f"(acc[e].x * gs), "f"(acc[e].y * gs), "f"(acc[e].z * gs), "f"(acc[e].w * gs) : "memory");
+            }
+        }
+    } else
     for (long long i0 = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; alive && i0 < hi; i0 += tstride * kElems) {
         float4 acc[kElems];
 #pragma unroll
@@ -226,8 +261,10 @@ extern "C" size_t osb_head_dw_allreduce_flag_bytes(int world) { return world < 1
 extern "C" int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,
                                      void* const* peer_flags, int rank, int world, int splits, int64_t n, int64_t split_stride,
                                      float* extra_out, int n_extra, int n_plain, const float* gscale, const double* den,
-                                     int max_ctas, void* stream) {
+                                     const void* mc_partials, void* mc_dw, int max_ctas, void* stream) {
     OSB_ENTRY_GUARD();
+    OSB_REQUIRE((mc_partials == nullptr) == (mc_dw == nullptr) && (uintptr_t)mc_partials % 16 == 0 && (uintptr_t)mc_dw % 16 == 0, OSB_ERR_ARG,
+                "osb_head_dw_allreduce: the multicast addresses come as a 16-byte aligned pair, or not at all");
     OSB_REQUIRE(peer_partials && peer_dw && peer_flags && den, OSB_ERR_ARG, "osb_head_dw_allreduce: null pointer");
     OSB_REQUIRE(world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world, OSB_ERR_ARG, "osb_head_dw_allreduce: bad rank %d / world %d", rank, world);
     OSB_REQUIRE(splits <= 16, OSB_ERR_ARG, "osb_head_dw_allreduce: at most 16 splits (got %d)", splits);
@@ -246,6 +283,7 @@ extern "C" int osb_head_dw_allreduce(const void* const* peer_partials, void* con
         p.extra_in[r] = n_extra ? reinterpret_cast<const float*>(peer_extra[r]) : nullptr;
         p.flags[r] = reinterpret_cast<unsigned int*>(peer_flags[r]);
     }
+    p.mc_partials = reinterpret_cast<const float*>(mc_partials); p.mc_out = reinterpret_cast<float*>(mc_dw);
     p.extra_out = extra_out; p.gscale = gscale; p.den = den; p.n = n; p.split_stride = split_stride;
     p.n_extra = n_extra; p.n_plain = n_plain; p.splits = splits; p.rank = rank; p.world = world;
     p.timeout_cycles = g_ar_timeout > 0 ? g_ar_timeout : 4000000000LL;        // ~2 s at 1.9 GHz

@@ -122,13 +122,14 @@ class PeerGradAllReduce:
         self.splits = 1 if self.local_reduce else self.gemm_splits
         self.n = n
         self.extra_sum = torch.zeros(max(self.n_extra, 1), dtype=torch.float32, device=plan.dev)
+        self.mc_partials = self.mc_dw = None          # multicast addresses (NVSwitch), set by from_symmetric_memory
         self.stream = torch.cuda.Stream(device=plan.dev)
         self._ready = torch.cuda.Event()
         self._done = torch.cuda.Event()
         self._keep = None
 
     @classmethod
-    def from_symmetric_memory(cls, B, K, C, variant, group=None, max_ctas=32, device=None, **plan_kwargs):
+    def from_symmetric_memory(cls, B, K, C, variant, group=None, max_ctas=32, device=None, multicast=True, **plan_kwargs):
         """Allocates workspace, gradient buffer, flags and denominator slots in symmetric memory and builds the
         ``HeadPlan`` on them."""
         import torch.distributed._symmetric_memory as symm_mem
@@ -152,6 +153,12 @@ class PeerGradAllReduce:
         plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=flat, workspace=wsb, n_tail=n_tail, **plan_kwargs)
         obj = cls(plan, handles[0].buffer_ptrs, handles[1].buffer_ptrs, handles[2].buffer_ptrs, rank, ws_, max_ctas=max_ctas)
         obj.slot_ptrs = (L.C.c_void_p * ws_)(*[int(p) for p in handles[3].buffer_ptrs])
+        # NVSwitch multicast mappings of the partials and of the gradient buffer, when the fabric offers them: the
+        # all-reduce then sums inside the switch (multimem.ld_reduce) and broadcasts with one store (multimem.st)
+        mc_ws = int(getattr(handles[0], "multicast_ptr", 0) or 0)
+        mc_flat = int(getattr(handles[1], "multicast_ptr", 0) or 0)
+        if multicast and mc_ws and mc_flat:
+            obj.mc_partials, obj.mc_dw = mc_ws + L.size("osb_head_dw_partials_offset"), mc_flat
         obj._keep = (wsb, flat, flags, slots, handles)
         return obj
 
@@ -161,7 +168,7 @@ class PeerGradAllReduce:
         st = L.stream_ptr(self.plan.dev) if stream is None else stream.cuda_stream
         L.call("osb_head_dw_allreduce", self._partials, self._dw, self._extra if self.n_extra else None, self._flags,
                self.rank, self.world, self.splits, self.n, self.n, L.ptr(self.extra_sum), self.n_extra, self.n_plain,
-               L.ptr(gscale), L.ptr(den), self.max_ctas, st)
+               L.ptr(gscale), L.ptr(den), self.mc_partials, self.mc_dw, self.max_ctas, st)
 
     def run(self, den, gscale=None):
         """dW GEMM partials must already be enqueued on the current stream.  Runs the all-reduce on the side stream
@@ -201,8 +208,8 @@ class ShardedHeadPlan:
     Without symmetric memory (``peer_allreduce=False``) the same step runs eagerly with NCCL collectives.
     """
 
-    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=16, device=None, peer_allreduce=False,
-                 **plan_kwargs):
+    def __init__(self, B, K, C, variant="entropic", group=None, sm_reserve=None, device=None, peer_allreduce=False,
+                 multicast=True, **plan_kwargs):
         from . import _lib as L
         from .functional import HeadPlan
         self.group = group
@@ -214,8 +221,13 @@ class ShardedHeadPlan:
         self.peer = None
         if peer_allreduce and self.world > 1:
             # dW all-reduce over NVLink peer memory fused with the split-K reduction (no NCCL on the data path)
-            self.peer = PeerGradAllReduce.from_symmetric_memory(B, K, C, variant, group=group, max_ctas=sm_reserve, device=dev,
-                                                                **plan_kwargs)
+            self.peer = PeerGradAllReduce.from_symmetric_memory(B, K, C, variant, group=group, max_ctas=sm_reserve or 16, device=dev,
+                                                                multicast=multicast, **plan_kwargs)
+            if sm_reserve is None:
+                # summed inside the NVSwitch the all-reduce moves 1/world of the bytes: 8 CTAs keep up with dX; with peer
+                # loads it is paced by NVLink round trips and takes 16
+                sm_reserve = 8 if self.peer.mc_partials is not None else 16
+                self.peer.max_ctas = sm_reserve
             self.plan = self.peer.plan
             self.flat = self.plan.flat
         else:
@@ -223,7 +235,7 @@ class ShardedHeadPlan:
             self.plan = HeadPlan(B, K, C, variant, device=dev, grad_buffer=self.flat, **plan_kwargs)
         self._L = L
         self._sms = L.size("osb_sm_count")
-        self.sm_reserve = int(sm_reserve) if self.world > 1 else 0
+        self.sm_reserve = int(sm_reserve or 16) if self.world > 1 else 0
         p = self.plan
         self.entropic = variant == "entropic"
         # global denominator: a constant for the entropic loss, the peer / NCCL sum of the shard denominators otherwise
