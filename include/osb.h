@@ -254,6 +254,21 @@ int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_type, int64
              double* ccr, double* fpr, int64_t* meta /* [5]: n_unique, n_known, n_correct, n_unk, n_bad */,
              void* ws, size_t ws_bytes, void* stream);
 
+/* ---- row-sharded OSCR over the GPUs of one box ---------------------------------------------------------------- *
+ * The reference evaluates on one device (script/plot_all.py:151-188); this is what a row-sharded evaluation set needs.
+ * osb_oscr_exchange (one launch per rank, after osb_oscr_records on the rank's rows): all-gather of the compacted
+ * records through NVLink peer memory.  Every rank's records land, in rank order, in EVERY rank's gathered arrays
+ * (peer_rec_unk[r] / peer_rec_known[r]: capacity `cap` records each, peer-mapped), and totals_global[4] (local, int64)
+ * receives the four stage-A totals summed over the ranks: pass totals_global + 2 / + 0 as n_a / n_b of osb_oscr_curve
+ * and totals_global[3] as n_bad.  Every rank then sorts identical inputs, so the curve is replicated and bit-identical
+ * to the single-GPU one.  peer_slots[r]: osb_oscr_exchange_slot_bytes(world) bytes per rank, peer-mapped, zeroed once
+ * (count words, done stamps and the epoch, which advances per launch: graph capturable).  A rank that waits ~2 s for a
+ * peer gives up: totals_global = {0, 0, 0, 2^40} (an impossible n_bad the caller must check).  HOST pointer tables. */
+size_t osb_oscr_exchange_slot_bytes(int world);
+int osb_oscr_exchange(const uint64_t* rec_unk, const uint64_t* rec_known, const int64_t* totals,
+                      void* const* peer_rec_unk, void* const* peer_rec_known, void* const* peer_slots,
+                      int rank, int world, int64_t cap, int64_t* totals_global, int max_ctas, void* stream);
+
 /* ---- CCR@FPR (script/plot_all.py:346-352,378-384) ------------------------------------------ *
  * For each of nq <= 16 queries q (host doubles): idx = first argmin_j |fpr[j]-q| over the
  * n_unique[0]-1 thresholds the reference keeps (NaN counts as the minimum, like numpy.argmin).

@@ -21,7 +21,7 @@ LIB = os.path.join(CSRC, "libosb.so")
 STAMP = os.path.join(CSRC, "libosb.stamp")
 LOG = os.path.join(CSRC, "libosb.build.log")
 OBJ_DIR = os.path.join(CSRC, "_obj")
-SOURCES = ["lib.cu", "loss_rows.cu", "confidence.cu", "oscr.cu", "hist.cu", "head_tc.cu", "dw_allreduce.cu"]
+SOURCES = ["lib.cu", "loss_rows.cu", "confidence.cu", "oscr.cu", "oscr_shard.cu", "hist.cu", "head_tc.cu", "dw_allreduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",

@@ -440,3 +440,94 @@ def calculate_oscr_sharded(gt, scores, unk_label=-1, group=None):
                cap, L.ptr(ccr), L.ptr(fpr), st)
     meta_g = torch.cat([meta[0:1], tot_g])
     return ccr, fpr, ccr_cnt, fpr_cnt, taus, meta_g
+
+
+class OscrShardedPlan:
+    """OSCR over a row-sharded evaluation set with persistent buffers and no NCCL on the data path: stage A on this
+    rank's rows, ONE peer-memory all-gather of the compacted records (``osb_oscr_exchange``), then the sort + scan on
+    every rank (identical inputs -> the curve is replicated and bit-identical to ``util.calculate_oscr`` on the
+    concatenated data).  Three launches, no allocation, no host synchronisation: capturable into a CUDA graph
+    (``capture``); every rank must run / replay the same number of times.
+
+    ``n_local``: rows of this rank's shard (the same on every rank; pad a ragged shard with rows labelled -3, which
+    belong to neither group).  Outputs (device tensors, overwritten by every call): ``ccr`` / ``fpr`` float64 and, with
+    ``counts=True``, ``taus`` float32, ``ccr_cnt`` / ``fpr_cnt`` int64, all of capacity ``n_local * world``;
+    ``meta`` int64 [5] = (n_unique, n_known, n_correct, n_unk, 0) and ``totals`` int64 [4] = global stage-A totals
+    (n_known, n_correct, n_unk, n_bad).  The reference's arrays are the first ``meta[0] - 1`` entries.
+    """
+
+    def __init__(self, n_local: int, C: int, unk_label: int = -1, group=None, device=None, counts: bool = True, max_ctas: int = 32):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        self._L = L
+        self.rank, self.world = world()
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n_local, self.C, self.unk_label, self.max_ctas = int(n_local), int(C), int(unk_label), int(max_ctas)
+        d, W = self.dev, self.world
+        self.cap = max(self.n_local * W, 1)
+        grp = group if group is not None else dist.group.WORLD
+        # gathered record arrays and the slot area live in symmetric (peer-mapped) memory
+        self.all_unk = symm_mem.empty(self.cap, dtype=torch.int64, device=d)
+        self.all_known = symm_mem.empty(self.cap, dtype=torch.int64, device=d)
+        self.slots = symm_mem.empty(L.size("osb_oscr_exchange_slot_bytes", W) // 4 + 4, dtype=torch.int32, device=d)
+        self.slots.zero_()
+        self._handles = [symm_mem.rendezvous(t, grp) for t in (self.all_unk, self.all_known, self.slots)]
+        torch.cuda.synchronize(d)
+        dist.barrier(group=group)
+        P = L.C.c_void_p * W
+        self._p_unk = P(*[int(p) for p in self._handles[0].buffer_ptrs])
+        self._p_known = P(*[int(p) for p in self._handles[1].buffer_ptrs])
+        self._p_slots = P(*[int(p) for p in self._handles[2].buffer_ptrs])
+        n1 = max(self.n_local, 1)
+        self.rec_unk = torch.empty(n1, dtype=torch.int64, device=d)
+        self.rec_known = torch.empty(n1, dtype=torch.int64, device=d)
+        self.totals_local = torch.zeros(4, dtype=torch.int64, device=d)
+        self.totals = torch.zeros(4, dtype=torch.int64, device=d)
+        self.taus = torch.empty(self.cap, dtype=torch.float32, device=d) if counts else None
+        self.ccr_cnt = torch.empty(self.cap, dtype=torch.int64, device=d) if counts else None
+        self.fpr_cnt = torch.empty(self.cap, dtype=torch.int64, device=d) if counts else None
+        self.ccr = torch.empty(self.cap, dtype=torch.float64, device=d)
+        self.fpr = torch.empty(self.cap, dtype=torch.float64, device=d)
+        self.meta = torch.zeros(5, dtype=torch.int64, device=d)
+        self.ws = torch.zeros(L.size("osb_oscr_curve_workspace_bytes", self.cap) + 256, dtype=torch.uint8, device=d)
+        self.launches_per_call = 3
+
+    def run(self, scores: torch.Tensor, gt: torch.Tensor):
+        from .util import _LABEL_TYPES
+        L = self._L
+        if scores.shape != (self.n_local, self.C) or scores.dtype != torch.float32 or scores.stride(1) != 1:
+            raise ValueError("scores must be this rank's float32 [n_local, C] shard with unit column stride")
+        if gt.shape != (self.n_local,) or gt.dtype not in _LABEL_TYPES or not gt.is_contiguous():
+            raise ValueError("gt must be a contiguous int64 / int32 / float32 [n_local] tensor")
+        st = L.stream_ptr(self.dev)
+        L.call("osb_oscr_records", L.ptr(scores), scores.stride(0) if self.n_local else self.C, L.ptr(gt), _LABEL_TYPES[gt.dtype],
+               self.n_local, self.C, self.unk_label, L.ptr(self.rec_unk), L.ptr(self.rec_known), L.ptr(self.totals_local), st)
+        L.call("osb_oscr_exchange", L.ptr(self.rec_unk), L.ptr(self.rec_known), L.ptr(self.totals_local), self._p_unk, self._p_known,
+               self._p_slots, self.rank, self.world, self.cap, L.ptr(self.totals), self.max_ctas, st)
+        L.call("osb_oscr_curve", L.ptr(self.all_unk), L.ptr(self.totals[2:3]), L.ptr(self.all_known), L.ptr(self.totals[0:1]), self.cap,
+               L.ptr(self.taus), L.ptr(self.ccr_cnt), L.ptr(self.fpr_cnt), L.ptr(self.ccr), L.ptr(self.fpr), L.ptr(self.meta),
+               L.ptr(self.ws), self.ws.numel(), st)
+        return self
+
+    def capture(self, scores: torch.Tensor, gt: torch.Tensor):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.run(scores, gt)                     # warm-up outside capture: one epoch of the exchange on every rank
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.run(scores, gt)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        return graph
+
+    def result(self):
+        """(ccr, fpr) float64 numpy arrays like ``util.calculate_oscr`` (one host sync); raises like it on bad labels."""
+        n_unique = int(self.meta[0].item())
+        n_bad = int(self.totals[3].item())
+        if n_bad >= (1 << 40):
+            raise RuntimeError("sharded OSCR: a rank gave up waiting for a peer during the record exchange")
+        if n_bad:
+            raise IndexError(f"{n_bad} label(s) out of bounds for axis 1 with size {self.C}")
+        n = max(n_unique - 1, 0)
+        return self.ccr[:n].cpu().numpy(), self.fpr[:n].cpu().numpy()

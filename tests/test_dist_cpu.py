@@ -102,7 +102,31 @@ def _head_worker(rank, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_oscr_worker, _head_worker])
+def _confidence_worker(rank, port, out_dir):
+    """the confidence of a row-sharded validation set = one all-reduce of 2 float64 sums + counts."""
+    _init(rank, port)
+    try:
+        from openset_imagenet_b200 import dist as D
+        from openset_imagenet_b200.metrics import finish_confidence
+        from oracle import oracle as O
+        n, C = 3000, 19
+        gt, s = O.make_oscr_case(n * WORLD, C, seed=5)
+        sl = slice(rank * n, (rank + 1) * n)
+        # stand-in for osb_confidence on this shard: the oracle's float64 sums and exact counts
+        _, kn_c, _, ng_c, kn_sum, ng_sum = O.confidence(s[sl], gt[sl], 1.0 / C, -1, None)
+        sums = torch.tensor([kn_sum, ng_sum], dtype=torch.float64)
+        counts = torch.tensor([kn_c, ng_c, 0], dtype=torch.int64)
+        g_sums, g_counts = D.allreduce_confidence(sums, counts)
+        got = finish_confidence(g_sums, g_counts, C)
+        want = O.confidence(s, gt, 1.0 / C, -1, None)
+        assert (got[1], got[3]) == (want[1], want[3])                      # counts exact
+        assert abs(got[0] - want[0]) < 1e-12 and abs(got[2] - want[2]) < 1e-12
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_oscr_worker, _head_worker, _confidence_worker])
 def test_world_size_2_gloo(worker, tmp_path):
     port = _free_port()
     mp.spawn(worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
