@@ -329,3 +329,72 @@ def test_get_histogram_large_and_empty_groups():
     for a, b in zip(got, ref):
         np.testing.assert_array_equal(a, b)
     assert got[2].sum() == 0
+
+
+def test_oscr_record_exchange_two_emulated_ranks_give_the_single_gpu_curve():
+    """osb_oscr_exchange (the peer-memory all-gather of the sharded path), two ranks emulated on ONE GPU: rank 1 runs first
+    with rank 0's count words and done stamp pre-published, then rank 0 finds rank 1's in its slot area.  Both gathered
+    arrays must hold [rank 0 records | rank 1 records], and the curve sorted from them is bit-identical to the single-GPU
+    one on the concatenated rows."""
+    from openset_imagenet_b200 import _lib as L
+    from openset_imagenet_b200.functional import OscrPlan
+    dev = torch.device("cuda")
+    n, C = 6000, 37
+    gt, s = O.make_oscr_case(2 * n, C, seed=23)
+    s[::5] = np.round(s[::5], 2)                                     # ties within and across the shards
+    st = L.stream_ptr(dev)
+    rec, tot = [], []
+    for r in range(2):
+        ru = torch.empty(n, dtype=torch.int64, device=dev); rk = torch.empty(n, dtype=torch.int64, device=dev)
+        t = torch.zeros(4, dtype=torch.int64, device=dev)
+        sc = torch.tensor(s[r * n:(r + 1) * n], device=dev); g = torch.tensor(gt[r * n:(r + 1) * n], device=dev)
+        L.call("osb_oscr_records", L.ptr(sc), C, L.ptr(g), L.LABEL_I64, n, C, -1, L.ptr(ru), L.ptr(rk), L.ptr(t), st)
+        rec.append((ru, rk)); tot.append(t)
+    torch.cuda.synchronize()
+    cap = 2 * n
+    all_u = [torch.full((cap,), -7, dtype=torch.int64, device=dev) for _ in range(2)]
+    all_k = [torch.full((cap,), -7, dtype=torch.int64, device=dev) for _ in range(2)]
+    nsl = L.size("osb_oscr_exchange_slot_bytes", 2) // 4 + 4
+    slots = [torch.zeros(nsl, dtype=torch.int32, device=dev) for _ in range(2)]
+    P = L.C.c_void_p * 2
+    pu, pk, ps = P(*[t.data_ptr() for t in all_u]), P(*[t.data_ptr() for t in all_k]), P(*[t.data_ptr() for t in slots])
+    # pre-publish rank 0 in rank 1's slot area: count words (value, epoch 1) at [rank 0][j], done stamp at [16 * 4 * 2 + 0]
+    t0 = tot[0].tolist()
+    for j in range(4):
+        slots[1][(0 * 4 + j) * 2] = t0[j]; slots[1][(0 * 4 + j) * 2 + 1] = 1
+    slots[1][16 * 4 * 2 + 0] = 1
+    tg = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+    for r in (1, 0):
+        L.call("osb_oscr_exchange", L.ptr(rec[r][0]), L.ptr(rec[r][1]), L.ptr(tot[r]), pu, pk, ps, r, 2, cap, L.ptr(tg[r]), 8, st)
+        torch.cuda.synchronize()
+    want_tot = (tot[0] + tot[1]).tolist()
+    for r in range(2):
+        assert tg[r].tolist() == want_tot
+        nk0, nk1, nu0, nu1 = int(tot[0][0]), int(tot[1][0]), int(tot[0][2]), int(tot[1][2])
+        assert torch.equal(all_k[r][:nk0].sort().values, rec[0][1][:nk0].sort().values)
+        assert torch.equal(all_k[r][nk0:nk0 + nk1].sort().values, rec[1][1][:nk1].sort().values)
+        assert torch.equal(all_u[r][:nu0].sort().values, rec[0][0][:nu0].sort().values)
+        assert torch.equal(all_u[r][nu0:nu0 + nu1].sort().values, rec[1][0][:nu1].sort().values)
+        assert bool((all_k[r][nk0 + nk1:] == -7).all()) and bool((all_u[r][nu0 + nu1:] == -7).all())
+    ref = OscrPlan(2 * n, C, -1).run(torch.tensor(s, device=dev), torch.tensor(gt, device=dev))
+    nu = int(ref.meta[0])
+    for r in range(2):
+        taus = torch.empty(cap, dtype=torch.float32, device=dev)
+        cc = torch.empty(cap, dtype=torch.int64, device=dev); fc = torch.empty(cap, dtype=torch.int64, device=dev)
+        ccr = torch.empty(cap, dtype=torch.float64, device=dev); fpr = torch.empty(cap, dtype=torch.float64, device=dev)
+        meta = torch.zeros(5, dtype=torch.int64, device=dev)
+        ws = torch.zeros(L.size("osb_oscr_curve_workspace_bytes", cap) + 256, dtype=torch.uint8, device=dev)
+        L.call("osb_oscr_curve", L.ptr(all_u[r]), L.ptr(tg[r][2:3]), L.ptr(all_k[r]), L.ptr(tg[r][0:1]), cap, L.ptr(taus), L.ptr(cc), L.ptr(fc),
+               L.ptr(ccr), L.ptr(fpr), L.ptr(meta), L.ptr(ws), ws.numel(), st)
+        torch.cuda.synchronize()
+        assert meta.tolist()[:4] == ref.meta.tolist()[:4]
+        assert torch.equal(taus[:nu], ref.taus[:nu]) and torch.equal(cc[:nu], ref.ccr_cnt[:nu]) and torch.equal(fc[:nu], ref.fpr_cnt[:nu])
+        assert torch.equal(ccr[:nu], ref.ccr[:nu]) and torch.equal(fpr[:nu], ref.fpr[:nu])
+    # a rank whose peer never shows up (epoch 2 words are missing) gives up and poisons n_bad
+    L.load().osb_debug_set_exchange_timeout(20_000_000)
+    try:
+        L.call("osb_oscr_exchange", L.ptr(rec[0][0]), L.ptr(rec[0][1]), L.ptr(tot[0]), pu, pk, ps, 0, 2, cap, L.ptr(tg[0]), 8, st)
+        torch.cuda.synchronize()
+    finally:
+        L.load().osb_debug_set_exchange_timeout(0)
+    assert int(tg[0][3]) >= (1 << 40) and int(tg[0][0]) == 0
