@@ -411,7 +411,8 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
                "h2d_bytes_per_step": B * K * 2 + B * 8, "d2h_bytes_per_step": 4,
                "ms_per_step": ems / n_e2e,
                "note": "features+labels copied from pinned host memory every step (prefetched one step ahead on a copy stream), "
-                       "loss read back every step; dX and dW stay on the device for the backbone / optimiser"}
+                       "loss read back every step; dX and dW stay on the device for the backbone / optimiser",
+               "host_thread_cpus": len(os.sched_getaffinity(0))}
     return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clocks, loss=loss_val,
                 launches=sp.launches_per_step * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
                 precision=parity.get("head", {}).get("precision"))
@@ -746,6 +747,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA (sm_100a) device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = False
+    if world > 1:
+        # host buffers and the threads that feed them next to this rank's GPU (the e2e leg copies 67 MB per step and rank)
+        from openset_imagenet_b200.dist import bind_host_thread_to_gpu_node
+        numa_bound = bind_host_thread_to_gpu_node(local)
     if world > 1:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):

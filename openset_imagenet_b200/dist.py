@@ -23,6 +23,21 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_thread_to_gpu_node(device_index: int | None = None) -> bool:
+    """Pin the calling host thread to the CPUs next to this rank's GPU (NVML's ideal CPU affinity) so that pinned host
+    buffers allocated afterwards -- and the copies out of them -- stay on the GPU's own NUMA node / PCIe root complex.
+    With eight ranks on a two-socket box the default placement sends most host-to-device copies across the socket
+    interconnect.  Returns False (and changes nothing) when NVML is not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+        return True
+    except Exception:
+        return False
+
+
 def world() -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

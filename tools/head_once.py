@@ -12,7 +12,7 @@ x = torch.randn(B, K, device=dev).bfloat16()
 w = (torch.randn(C, K, device=dev) / K ** 0.5).bfloat16()
 y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=1), device=dev)
 from openset_imagenet_b200 import _lib as L
-plan = HeadPlan(B, K, C, device=dev)
+plan = HeadPlan(B, K, C, device=dev, precision=os.environ.get("OSB_PRECISION", "fast"))
 for _ in range(reps):
     out = plan.step(x, w, y)
 torch.cuda.synchronize()
