@@ -254,6 +254,17 @@ int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_type, int64
              double* ccr, double* fpr, int64_t* meta /* [5]: n_unique, n_known, n_correct, n_unk, n_bad */,
              void* ws, size_t ws_bytes, void* stream);
 
+/* OSCR and metrics.confidence of the same evaluation set in ONE pass over the scores (script/plot_all.py:363-372 calls
+ * util.calculate_oscr and metrics.confidence on the same `values` with unknown_class = unk_label): osb_oscr plus
+ *   conf_sums[2] (double) {sum over known rows of s[i, y_i],
+ *                          sum over unk_label rows of float32(1 + offset) - max_c s[i, :valid_cols]}
+ * exactly as osb_confidence defines them (fixed summation order, bit-reproducible); the counts of metrics.confidence are
+ * meta[1] (kn_count) and meta[3] (neg_count), out-of-range labels meta[4].  unk_label must be negative. */
+int osb_oscr_with_confidence(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+                             int64_t unk_label, float one_plus_offset, int valid_cols,
+                             float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt, double* ccr, double* fpr,
+                             int64_t* meta, double* conf_sums, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- row-sharded OSCR over the GPUs of one box ---------------------------------------------------------------- *
  * The reference evaluates on one device (script/plot_all.py:151-188); this is what a row-sharded evaluation set needs.
  * osb_oscr_exchange (one launch per rank, after osb_oscr_records on the rank's rows): all-gather of the compacted

@@ -56,6 +56,7 @@ SIGNATURES = {
     "osb_oscr_curve": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "osb_oscr_ratios": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "osb_oscr": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "osb_oscr_with_confidence": (_i, [_p, _i64, _p, _i, _i64, _i, _i64, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "osb_oscr_exchange_slot_bytes": (_sz, [_i]),
     "osb_oscr_exchange": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _i, _p]),
     "osb_ccr_at_fpr": (_i, [_p, _p, _p, _i64, _p, _i, _p, _p, _p, _p]),

@@ -53,6 +53,17 @@ constexpr int kRecCtasPerSm = 2;
 constexpr size_t kRecStageBudget = 92 * 1024;   // bulk-copy stages per CTA (2 x (92 KB + 16.5 KB staging) fits one SM)
 constexpr int kMaxStages = 8;
 
+// Optional by-product of stage A: the two sums of metrics.confidence (metrics.py:33,36-40) over the same rows, for callers
+// that want the confidence of the evaluation set together with its OSCR curve (script/plot_all.py:363-372 computes both
+// from the same score matrix).  sums_out == nullptr switches it off.
+struct ConfAcc {
+    double* sums_out;            // [2]: sum over known rows of s[i, y_i];  sum over unk rows of float32(1 + offset) - max s[i, :valid_cols]
+    double* partials;            // [2 * grid] block partials (fixed-order final sum: bit-reproducible)
+    unsigned int* ticket;        // zero between calls
+    float one_plus_offset;
+    int valid_cols;
+};
+
 struct RecShared {
     uint64_t recK[kStageCap];
     uint64_t recU[kStageCap];
@@ -81,7 +92,8 @@ template <typename L, int LPR, bool TMA, bool ALIGNED>
 __global__ void __launch_bounds__(kRecThreads, kRecCtasPerSm)
 oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __restrict__ gt, int64_t N, int C,
                     int R, int S, int64_t unk_label, bool vec4,
-                    uint64_t* __restrict__ recU, uint64_t* __restrict__ recK, unsigned long long* __restrict__ totals, int dbg) {
+                    uint64_t* __restrict__ recU, uint64_t* __restrict__ recK, unsigned long long* __restrict__ totals, int dbg,
+                    const ConfAcc conf) {
     constexpr int RPW = 32 / LPR;
     extern __shared__ __align__(128) uint8_t rec_smem[];
     const uint32_t stage_bytes = TMA ? (uint32_t)R * (uint32_t)C * 4u : 0u;
@@ -115,6 +127,9 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
         for (int k = 0; k < S; ++k) issue((int)blockIdx.x + k * G, k);
 
     unsigned n_ok = 0, n_bad = 0;
+    double c_kn = 0.0, c_neg = 0.0;                            // confidence sums of this thread's rows (lanes with sub == 0)
+    const bool want_conf = conf.sums_out != nullptr;
+    const bool conf_cut = want_conf && conf.valid_cols < C;    // the negatives' maximum skips trailing columns (garbage class)
     int s = 0;
     uint32_t phase = 0;
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += G) {
@@ -145,7 +160,28 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
             if (TMA) {
                 const float* row = sbase + r * C;
                 float m_lo; int head, jb;
-                smem_row_split_max<LPR, ALIGNED>(row, C, known ? lab : -1, known || unk, sub, m_lo, m, head, jb);
+                // the split column: the label of a known row; for an unk row whose confidence maximum stops at valid_cols,
+                // that column (m_lo is then the maximum over the whole groups before it)
+                const int split = known ? lab : ((unk && conf_cut) ? conf.valid_cols : -1);
+                smem_row_split_max<LPR, ALIGNED>(row, C, split, known || unk, sub, m_lo, m, head, jb);
+                if (unk && want_conf && sub == 0) {
+                    float mv = m;
+                    if (conf_cut) {
+                        mv = m_lo;
+                        if (ALIGNED) {
+                            const float4 g4 = reinterpret_cast<const float4*>(row)[split >> 2];
+                            const int q = split & 3;
+                            if (q > 0) mv = fmaxf(mv, g4.x);
+                            if (q > 1) mv = fmaxf(mv, g4.y);
+                            if (q > 2) mv = fmaxf(mv, g4.z);
+                        } else {
+                            const int c0 = split < head ? split : head + 4 * jb;
+#pragma unroll 1
+                            for (int c = c0; c < split; ++c) mv = fmaxf(mv, row[c]);
+                        }
+                    }
+                    c_neg += (double)(conf.one_plus_offset - mv);          // float32 subtraction as torch does it (metrics.py:37-40)
+                }
                 if (known && sub == 0) {
                     ts = row[lab];                                 // util.py:111
                     ok = (ts > m_lo) && (ts == m);                 // first arg-max == gt (util.py:109,114) ...
@@ -164,7 +200,13 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
                 group_row_argmax<LPR>(scores + (row0 + r) * ld, C, known || unk, vec4, sub, m, am);      // util.py:109-110
                 if (am == 0x7fffffff) am = 0;                      // a row of -inf: numpy's argmax is 0
                 if (known && sub == 0) { ts = scores[(row0 + r) * ld + lab]; ok = (am == lab); }
+                if (want_conf) {                                   // (this variant is the rare strided / unaligned fallback)
+                    float mv = m; int amv;
+                    if (conf_cut) group_row_argmax<LPR>(scores + (row0 + r) * ld, conf.valid_cols, unk, vec4, sub, mv, amv);
+                    if (unk && sub == 0) c_neg += (double)(conf.one_plus_offset - mv);
+                }
             }
+            if (want_conf && known && sub == 0) c_kn += (double)ts;       // metrics.py:33
             if (sub == 0 && !(dbg & 1)) {
                 if (known) {
                     const unsigned p = atomicAdd(&sh.nK, 1u);
@@ -201,6 +243,18 @@ oscr_records_kernel(const float* __restrict__ scores, int64_t ld, const L* __res
     if (tid == 0) {
         if (sh.n_ok) atomicAdd(totals + 1, (unsigned long long)sh.n_ok);
         if (sh.n_bad) atomicAdd(totals + 3, (unsigned long long)sh.n_bad);
+    }
+    if (want_conf) {
+        // fixed tree inside the warp, warps in order, blocks in order by the last one out: bit-reproducible for a given grid
+        __shared__ double s_conf[2][kRecWarps];
+        c_kn = warp_sum(c_kn); c_neg = warp_sum(c_neg);
+        if (lane == 0) { s_conf[0][warp] = c_kn; s_conf[1][warp] = c_neg; }
+        __syncthreads();
+        double mine[2] = {0.0, 0.0};
+        if (tid == 0)
+            for (int w = 0; w < kRecWarps; ++w) { mine[0] += s_conf[0][w]; mine[1] += s_conf[1][w]; }
+        double tot[2];
+        if (last_block_reduce<2>(mine, conf.partials, conf.ticket, tot)) { conf.sums_out[0] = tot[0]; conf.sums_out[1] = tot[1]; }
     }
 }
 
@@ -778,23 +832,23 @@ static RecPlan plan_records(const float* scores, int64_t ld, const L* gt, int64_
 
 template <typename L, int LPR, bool TMA, bool ALIGNED>
 static int launch_records_k(const RecPlan& pl, const float* scores, int64_t ld, const L* gt, int64_t N, int C, int64_t unk_label,
-                            uint64_t* recU, uint64_t* recK, unsigned long long* totals, cudaStream_t st) {
+                            uint64_t* recU, uint64_t* recK, unsigned long long* totals, const ConfAcc& conf, cudaStream_t st) {
     auto k = oscr_records_kernel<L, LPR, TMA, ALIGNED>;
     static size_t smem_set = 0;                                  // per instantiation
     if (pl.smem > smem_set) {
         OSB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         smem_set = pl.smem;
     }
-    k<<<pl.grid, kRecThreads, pl.smem, st>>>(scores, ld, gt, N, C, pl.R, pl.S, unk_label, pl.vec4, recU, recK, totals, g_rec_debug);
+    k<<<pl.grid, kRecThreads, pl.smem, st>>>(scores, ld, gt, N, C, pl.R, pl.S, unk_label, pl.vec4, recU, recK, totals, g_rec_debug, conf);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
 
 template <typename L>
 static int launch_records(const float* scores, int64_t ld, const L* gt, int64_t N, int C, int64_t unk_label,
-                          uint64_t* recU, uint64_t* recK, unsigned long long* totals, cudaStream_t st) {
+                          uint64_t* recU, uint64_t* recK, unsigned long long* totals, const ConfAcc& conf, cudaStream_t st) {
     const RecPlan pl = plan_records(scores, ld, gt, N, C);
-#define OSB_REC(LPR_, TMA_, AL_) return launch_records_k<L, LPR_, TMA_, AL_>(pl, scores, ld, gt, N, C, unk_label, recU, recK, totals, st)
+#define OSB_REC(LPR_, TMA_, AL_) return launch_records_k<L, LPR_, TMA_, AL_>(pl, scores, ld, gt, N, C, unk_label, recU, recK, totals, conf, st)
     if (pl.tma) {
         if (pl.lpr == 4) OSB_REC(4, true, true);
         if (pl.lpr == 8) { if (pl.aligned) OSB_REC(8, true, true); OSB_REC(8, true, false); }
@@ -807,12 +861,15 @@ static int launch_records(const float* scores, int64_t ld, const L* gt, int64_t 
 }
 
 static int run_records(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C, int64_t unk_label,
-                       uint64_t* recU, uint64_t* recK, unsigned long long* totals, cudaStream_t st) {
-    if (N == 0) return OSB_OK;
+                       uint64_t* recU, uint64_t* recK, unsigned long long* totals, cudaStream_t st, const ConfAcc& conf = ConfAcc{}) {
+    if (N == 0) {
+        if (conf.sums_out) OSB_CUDA(cudaMemsetAsync(conf.sums_out, 0, 2 * sizeof(double), st));
+        return OSB_OK;
+    }
     switch (gt_type) {
-        case OSB_LABEL_I64: return launch_records(scores, ld, reinterpret_cast<const int64_t*>(gt), N, C, unk_label, recU, recK, totals, st);
-        case OSB_LABEL_F32: return launch_records(scores, ld, reinterpret_cast<const float*>(gt), N, C, unk_label, recU, recK, totals, st);
-        case OSB_LABEL_I32: return launch_records(scores, ld, reinterpret_cast<const int32_t*>(gt), N, C, unk_label, recU, recK, totals, st);
+        case OSB_LABEL_I64: return launch_records(scores, ld, reinterpret_cast<const int64_t*>(gt), N, C, unk_label, recU, recK, totals, conf, st);
+        case OSB_LABEL_F32: return launch_records(scores, ld, reinterpret_cast<const float*>(gt), N, C, unk_label, recU, recK, totals, conf, st);
+        case OSB_LABEL_I32: return launch_records(scores, ld, reinterpret_cast<const int32_t*>(gt), N, C, unk_label, recU, recK, totals, conf, st);
     }
     set_error("osb_oscr: bad label type %d", gt_type);
     return OSB_ERR_ARG;
@@ -891,9 +948,10 @@ extern "C" void osb_debug_set_records_mode(int m) { g_rec_debug = m; }
 // between calls (totals, barrier counters, digit histograms) sits at FIXED offsets at the front, so one workspace
 // serves calls of any size.
 extern "C" size_t osb_oscr_curve_workspace_bytes(int64_t cap) { return cap < 0 ? 0 : curve_ws_bytes(cap); }
+constexpr size_t kConfAreaBytes = 128 + 2 * sizeof(double) * 1024;      // ticket + block partials of the optional confidence sums
 extern "C" size_t osb_oscr_workspace_bytes(int64_t N) {
     if (N < 0) return 0;
-    return 256 + curve_ws_bytes(N) + 2 * align_up((size_t)(N > 0 ? N : 1) * sizeof(uint64_t), 256);
+    return 256 + curve_ws_bytes(N) + 2 * align_up((size_t)(N > 0 ? N : 1) * sizeof(uint64_t), 256) + kConfAreaBytes;
 }
 
 static int check_oscr_sizes(const char* fn, int64_t N, int C, int64_t ld) {
@@ -975,15 +1033,15 @@ extern "C" int osb_oscr_ratios(const int64_t* ccr_cnt, const int64_t* fpr_cnt, c
     return OSB_OK;
 }
 
-extern "C" int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
-                        int64_t unk_label, float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt,
-                        double* ccr, double* fpr, int64_t* meta, void* ws, size_t ws_bytes, void* stream) {
-    OSB_ENTRY_GUARD();
-    OSB_REQUIRE(meta && ws, OSB_ERR_ARG, "osb_oscr: null pointer");
-    int rc = check_oscr_sizes("osb_oscr", N, C, ld);
+static int oscr_impl(const char* fn, const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+                     int64_t unk_label, float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt,
+                     double* ccr, double* fpr, int64_t* meta, double* conf_sums, float one_plus_offset, int valid_cols,
+                     void* ws, size_t ws_bytes, void* stream) {
+    OSB_REQUIRE(meta && ws, OSB_ERR_ARG, "%s: null pointer", fn);
+    int rc = check_oscr_sizes(fn, N, C, ld);
     if (rc) return rc;
-    OSB_REQUIRE(N == 0 || (scores && gt && ccr && fpr), OSB_ERR_ARG, "osb_oscr: null pointer");
-    OSB_REQUIRE(ws_bytes >= osb_oscr_workspace_bytes(N), OSB_ERR_WORKSPACE, "osb_oscr: workspace too small (%zu < %zu)",
+    OSB_REQUIRE(N == 0 || (scores && gt && ccr && fpr), OSB_ERR_ARG, "%s: null pointer", fn);
+    OSB_REQUIRE(ws_bytes >= osb_oscr_workspace_bytes(N), OSB_ERR_WORKSPACE, "%s: workspace too small (%zu < %zu)", fn,
                 ws_bytes, osb_oscr_workspace_bytes(N));
     cudaStream_t st = (cudaStream_t)stream;
     char* p = reinterpret_cast<char*>(ws);
@@ -994,10 +1052,38 @@ extern "C" int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_
     const size_t rec_bytes = align_up((size_t)(N > 0 ? N : 1) * sizeof(uint64_t), 256);
     uint64_t* rec_unk = reinterpret_cast<uint64_t*>(p); p += rec_bytes;
     uint64_t* rec_known = reinterpret_cast<uint64_t*>(p); p += rec_bytes;
-    rc = run_records(scores, ld, gt, gt_type, N, C, unk_label, rec_unk, rec_known, totals, st);
+    ConfAcc conf = {};
+    if (conf_sums) {
+        conf.sums_out = conf_sums;
+        conf.ticket = reinterpret_cast<unsigned int*>(p);
+        conf.partials = reinterpret_cast<double*>(p + 128);
+        conf.one_plus_offset = one_plus_offset;
+        conf.valid_cols = valid_cols;
+    }
+    rc = run_records(scores, ld, gt, gt_type, N, C, unk_label, rec_unk, rec_known, totals, st, conf);
     if (rc != OSB_OK) return rc;
     return run_curve(rec_unk, reinterpret_cast<const int64_t*>(totals + 2), rec_known, reinterpret_cast<const int64_t*>(totals + 0), N,
                      taus, ccr_cnt, fpr_cnt, ccr, fpr, meta, totals, curve_ws, st);
+}
+
+extern "C" int osb_oscr(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+                        int64_t unk_label, float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt,
+                        double* ccr, double* fpr, int64_t* meta, void* ws, size_t ws_bytes, void* stream) {
+    OSB_ENTRY_GUARD();
+    return oscr_impl("osb_oscr", scores, ld, gt, gt_type, N, C, unk_label, taus, ccr_cnt, fpr_cnt, ccr, fpr, meta, nullptr, 0.f, C,
+                     ws, ws_bytes, stream);
+}
+
+extern "C" int osb_oscr_with_confidence(const float* scores, int64_t ld, const void* gt, int gt_type, int64_t N, int C,
+                                        int64_t unk_label, float one_plus_offset, int valid_cols,
+                                        float* taus, int64_t* ccr_cnt, int64_t* fpr_cnt, double* ccr, double* fpr,
+                                        int64_t* meta, double* conf_sums, void* ws, size_t ws_bytes, void* stream) {
+    OSB_ENTRY_GUARD();
+    OSB_REQUIRE(conf_sums, OSB_ERR_ARG, "osb_oscr_with_confidence: null conf_sums");
+    OSB_REQUIRE(unk_label < 0, OSB_ERR_ARG, "osb_oscr_with_confidence: unk_label must be negative (a row is then known or unk, never both)");
+    OSB_REQUIRE(valid_cols >= 1 && valid_cols <= C, OSB_ERR_ARG, "osb_oscr_with_confidence: valid_cols=%d outside [1,%d]", valid_cols, C);
+    return oscr_impl("osb_oscr_with_confidence", scores, ld, gt, gt_type, N, C, unk_label, taus, ccr_cnt, fpr_cnt, ccr, fpr, meta,
+                     conf_sums, one_plus_offset, valid_cols, ws, ws_bytes, stream);
 }
 
 extern "C" int osb_ccr_at_fpr(const double* ccr, const double* fpr, const int64_t* n_unique, int64_t n,

@@ -138,6 +138,77 @@ def calculate_oscr(gt, scores, unk_label=-1):
     return ccr, fpr
 
 
+def calculate_oscr_and_confidence_device(gt, scores, unk_label=-2, offset=0., last_valid_class=None, device=None):
+    """OSCR and ``metrics.confidence(scores, gt, offset, unknown_class=unk_label, last_valid_class)`` of the same
+    evaluation set from ONE pass over the score matrix (``osb_oscr_with_confidence``).  Returns
+    ``(OscrDeviceResult, conf_sums)`` with ``conf_sums`` float64 [2] on the device; the confidence counts are
+    ``meta[1]`` (known) and ``meta[3]`` (rows labelled ``unk_label``).  ``unk_label`` must be negative."""
+    if isinstance(scores, torch.Tensor) and scores.is_cuda:
+        dev = scores.device
+    else:
+        dev = torch.device(device) if device is not None else default_device()
+    s = _to_device(scores, dev, torch.float32)
+    if s.dim() != 2:
+        raise ValueError(f"scores must be [samples, classes], got {tuple(s.shape)}")
+    if s.stride(1) != 1 and s.shape[1] > 1:
+        s = s.contiguous()
+    g = _to_device(gt, dev)
+    if g.dtype not in _LABEL_TYPES:
+        g = g.to(torch.int64)
+    g = g.contiguous()
+    N, Cc = s.shape
+    if g.dim() != 1 or g.shape[0] != N:
+        raise ValueError(f"gt must be [samples]={N}, got {tuple(g.shape)}")
+    if int(unk_label) >= 0:
+        raise ValueError("the one-pass table needs a negative unk_label (a row is then known or unknown, never both)")
+    valid_cols = len(range(Cc)[slice(None, last_valid_class)])
+    one_plus_offset = float(torch.tensor(1.0 + offset, dtype=torch.float32))
+    with torch.cuda.device(dev):
+        cap = max(N, 1)
+        taus = torch.empty(cap, dtype=torch.float32, device=dev)
+        ccr_cnt = torch.empty(cap, dtype=torch.int64, device=dev)
+        fpr_cnt = torch.empty(cap, dtype=torch.int64, device=dev)
+        ccr = torch.empty(cap, dtype=torch.float64, device=dev)
+        fpr = torch.empty(cap, dtype=torch.float64, device=dev)
+        meta = torch.zeros(5, dtype=torch.int64, device=dev)
+        conf_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        ws = L.workspace("oscr", L.size("osb_oscr_workspace_bytes", N), dev)
+        L.call("osb_oscr_with_confidence", L.ptr(s), s.stride(0) if N else Cc, L.ptr(g), _LABEL_TYPES[g.dtype], N, Cc, int(unk_label),
+               one_plus_offset, valid_cols, L.ptr(taus), L.ptr(ccr_cnt), L.ptr(fpr_cnt), L.ptr(ccr), L.ptr(fpr), L.ptr(meta),
+               L.ptr(conf_sums), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    return OscrDeviceResult(taus, ccr_cnt, fpr_cnt, ccr, fpr, meta), conf_sums
+
+
+def conf_and_ccr(gt, scores, loss="entropic", unk_label=-2, queries=(1e-3, 1e-2, 0.1, 1.0)):
+    """The numbers of one row of the reference's result table (script/plot_all.py:344-387, ``conf_and_ccr_table``) from
+    one pass over the scores: ``(confidence, ccr_at)`` with ``confidence = (kn_conf, kn_count, neg_conf, neg_count)``
+    as ``metrics.confidence`` returns it for ``offset = 0 if loss == 'garbage' else 1 / (max(gt) + 1)``,
+    ``unknown_class = unk_label``, ``last_valid_class = -1 if loss == 'garbage' else None`` (plot_all.py:366-372), and
+    ``ccr_at`` = one entry per query q: ``ccr[argmin |fpr - q|]``, or None where the reference prints '---'
+    (``round(100 * |fpr - q| / q, 1) >= 10``, plot_all.py:378-384)."""
+    gt_t = gt if isinstance(gt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(gt))
+    n_cls = int(gt_t.max()) + 1                                    # numpy.max(gt) + 1, plot_all.py:366 (one small reduction)
+    offset = 0. if loss == "garbage" else 1. / n_cls
+    last_valid_class = -1 if loss == "garbage" else None
+    r, sums = calculate_oscr_and_confidence_device(gt, scores, unk_label, offset, last_valid_class)
+    n_q = len(queries)
+    if scores.shape[0] == 0:
+        raise AttributeError("'int' object has no attribute 'item'")
+    idx, f_at, c_at = ccr_at_fpr_device(r.ccr, r.fpr, r.meta[0:1], queries)
+    n_unique, n_known, _, n_unk, n_bad = r.meta.tolist()              # the one host sync
+    if n_bad:
+        raise IndexError(f"{n_bad} label(s) out of bounds for axis 1 with size {scores.shape[1]}")
+    s0, s1 = sums.tolist()
+    confidence = (s0 / n_known if n_known else 0.0, n_known, s1 / n_unk if n_unk else 0.0, n_unk)
+    if n_unique - 1 <= 0:
+        raise ValueError("attempt to get argmin of an empty sequence")
+    out = []
+    for q, fv, cv in zip(queries, f_at.tolist()[:n_q], c_at.tolist()[:n_q]):
+        err = round(100 * abs(fv - q) / q, 1)
+        out.append(None if err >= 10.0 else cv)
+    return confidence, out
+
+
 def ccr_at_fpr_device(ccr: torch.Tensor, fpr: torch.Tensor, n_unique: torch.Tensor, queries):
     """First argmin |fpr - q| per query on the device; returns (idx int64, fpr_at, ccr_at) tensors."""
     dev = L.require_cuda(ccr, fpr, n_unique)

@@ -398,3 +398,48 @@ def test_oscr_record_exchange_two_emulated_ranks_give_the_single_gpu_curve():
     finally:
         L.load().osb_debug_set_exchange_timeout(0)
     assert int(tg[0][3]) >= (1 << 40) and int(tg[0][0]) == 0
+
+
+@pytest.mark.parametrize("N,C,loss", [(20000, 116, "entropic"), (20000, 117, "garbage"), (5000, 10, "garbage"), (3001, 1000, "entropic"),
+                                        (70000, 152, "garbage")])
+def test_one_pass_table_is_oscr_plus_confidence(N, C, loss):
+    """script/plot_all.py:363-372 runs util.calculate_oscr and metrics.confidence over the same scores; the one-pass entry
+    must give the same curve bit for bit and the confidence of the oracle (counts exact, float64 sums to 1e-9)."""
+    import openset_imagenet_b200 as osb
+    from openset_imagenet_b200.util import calculate_oscr_and_confidence_device, calculate_oscr_device, conf_and_ccr
+    n_known = C - 1 if loss == "garbage" else C
+    gt, s = O.make_oscr_case(N, C, seed=N + C)
+    gt = np.where(gt >= n_known, n_known - 1, gt)                    # the garbage column is never a label of a test sample
+    gt[0] = n_known - 1                                              # so that numpy.max(gt) + 1 is the class count
+    offset = 0. if loss == "garbage" else 1. / n_known
+    lvc = -1 if loss == "garbage" else None
+    r, sums = calculate_oscr_and_confidence_device(gt, s, -2, offset, lvc)
+    ref = calculate_oscr_device(gt, s, -2)
+    nu = int(ref.meta[0])
+    assert r.meta.tolist() == ref.meta.tolist()
+    for a, b in ((r.taus, ref.taus), (r.ccr_cnt, ref.ccr_cnt), (r.fpr_cnt, ref.fpr_cnt), (r.ccr, ref.ccr), (r.fpr, ref.fpr)):
+        assert torch.equal(a[:nu], b[:nu])
+    kn, n_kn, ng, n_ng, kn_sum, ng_sum = O.confidence(s, gt, offset, -2, lvc)
+    assert (int(r.meta[1]), int(r.meta[3])) == (n_kn, n_ng)
+    got = sums.tolist()
+    assert got[0] == pytest.approx(kn_sum, rel=1e-12, abs=1e-9) and got[1] == pytest.approx(ng_sum, rel=1e-12, abs=1e-9)
+    # the table row against the two separate drop-in calls
+    conf, ccr_at = conf_and_ccr(gt, s, loss=loss, unk_label=-2)
+    want_conf = osb.confidence(torch.tensor(s, device="cuda"), torch.tensor(gt, device="cuda"), offset, -2, lvc)
+    assert conf[1] == want_conf[1] and conf[3] == want_conf[3]
+    assert conf[0] == pytest.approx(want_conf[0], rel=1e-12) and conf[2] == pytest.approx(want_conf[2], rel=1e-12)
+    ccr, fpr = _calc(gt, s, -2)
+    want_at = [v for _, _, v in osb.ccr_at_fpr(ccr, fpr)]
+    assert ccr_at == want_at
+
+
+def test_one_pass_table_strided_input_takes_the_fallback_row_reduce():
+    from openset_imagenet_b200.util import calculate_oscr_and_confidence_device
+    gt, s = O.make_oscr_case(4000, 37, seed=3)
+    wide = torch.zeros(4000, 41, device="cuda")
+    wide[:, :37] = torch.tensor(s, device="cuda")
+    r, sums = calculate_oscr_and_confidence_device(gt, wide[:, :37], -1, 0., -1)     # row pitch 41: no bulk copies
+    _, n_kn, _, n_ng, kn_sum, ng_sum = O.confidence(s, gt, 0., -1, -1)
+    assert (int(r.meta[1]), int(r.meta[3])) == (n_kn, n_ng)
+    got = sums.tolist()
+    assert got[0] == pytest.approx(kn_sum, rel=1e-12, abs=1e-9) and got[1] == pytest.approx(ng_sum, rel=1e-12, abs=1e-9)
