@@ -546,3 +546,51 @@ def test_peer_sum_world_1_and_emulated_pair():
     L.call("osb_peer_sum", L.ptr(v0), L.ptr(o), 1, two, 0, 2, L.stream_ptr(torch.device("cuda")))
     torch.cuda.synchronize()
     assert float(o[0]) == 10.5                                   # rank 0 finds rank 1's epoch-1 words waiting
+
+
+# ---- the autograd flavour of the sharded head (dist.ShardedHead), two ranks sharing ONE GPU over gloo -------------------
+def _sharded_head_worker(rank, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    try:
+        from openset_imagenet_b200 import dist as D
+        from openset_imagenet_b200.model import FusedOpenSetHead
+        torch.cuda.set_device(0)
+        B, K, C = 384, 256, 40
+        for variant in ("entropic", "garbage"):
+            x, W, b, y, cw = _case(2 * B, K, C, variant, 77, True)
+            head = FusedOpenSetHead(K, C, bias=True, variant=variant, device=DEV,
+                                    class_weights=None if cw is None else torch.tensor(cw, device=DEV))
+            with torch.no_grad():
+                head.weight.copy_(torch.tensor(W)); head.bias.copy_(torch.tensor(b))
+            sh = D.ShardedHead(head)
+            sl = slice(rank * B, (rank + 1) * B)
+            xt = torch.tensor(x[sl], device=DEV, requires_grad=True)
+            local = sh.loss(xt, torch.tensor(y[sl], device=DEV))           # this shard's numerator over the GLOBAL denominator
+            local.backward()
+            _, unpack = sh.allreduce_grads(local)
+            full_loss = float(unpack())
+            ov = {"entropic": O.ENTROPIC, "garbage": O.GARBAGE}[variant]
+            ref = O.head_fwd_bwd(x, W, b, y, ov, class_weights=cw)          # the whole batch on one device
+            assert full_loss == pytest.approx(ref["loss"], rel=TOL)
+            assert _rel(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL
+            assert _rel(head.bias.grad.cpu().numpy(), ref["db"]) < TOL
+            assert _rel(xt.grad.cpu().numpy(), ref["dx"][sl]) < TOL        # d(full loss) / d(local features)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_head_autograd_two_ranks_on_one_gpu(tmp_path):
+    """dist.ShardedHead: the loss denominator is all-reduced before the forward kernel, every rank back-propagates its
+    shard, one all-reduce of [dW | db | loss] gives the full-batch gradients -- against the oracle on the whole batch.
+    Two processes share cuda:0 and talk over gloo (the driver's GPU box has one GPU for the tests)."""
+    import os, socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_head_worker, args=(port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(2))

@@ -10,7 +10,7 @@ B, K, C = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (16384, 2048
 x = torch.randn(B, K, device=dev).bfloat16()
 w = (torch.randn(C, K, device=dev) / K ** 0.5).bfloat16()
 y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=1), device=dev)
-plan = HeadPlan(B, K, C, device=dev)
+plan = HeadPlan(B, K, C, device=dev, precision="fast")
 lib = L.load()
 lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
 trace = torch.zeros(512, 64, dtype=torch.int64, device=dev)
