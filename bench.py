@@ -705,7 +705,7 @@ def main():
     ap.add_argument("--no-oscr", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the bg / resnet sub-objects of the default line")
     ap.add_argument("--sm-reserve", type=int, default=0, help="SMs left to the gradient all-reduce while dX runs (N > 1); "
-                    "0 = 8 with NVSwitch multicast, 16 with peer loads")
+                    "0 = 16")
     ap.add_argument("--no-multicast", action="store_true", help="all-reduce with peer loads instead of NVSwitch multimem (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -96,32 +96,44 @@ dw_allreduce_kernel(const ArParams p) {
         // NVSwitch path: ONE multimem.ld_reduce per element and split returns the sum over all ranks, added inside the switch
         // (1 / world of the peer-load traffic and round trips); ONE multimem.st writes the result into every rank's dW.
         // Each element is still reduced once, by its owner, so all ranks hold bit-identical gradients.
+        // The switch answers a multimem.ld_reduce in a few microseconds, so throughput = bytes in flight / that latency:
+        // every thread keeps kMc elements of (up to) TWO splits in flight at once -- 8 x 16 bytes, 128 KB per CTA.
         constexpr int kMc = 4;
         const float4* mc_in = reinterpret_cast<const float4*>(p.mc_partials);
         float4* mc_o = reinterpret_cast<float4*>(p.mc_out);
+        auto ldr = [](const float4* a) {
+            float4 v;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
+            return v;
+        };
         for (long long i0 = lo + (long long)blockIdx.x * kArThreads + threadIdx.x; alive && i0 < hi; i0 += tstride * kMc) {
-            float4 acc[kMc];
+            float4 v0[kMc], v1[kMc];
 #pragma unroll
-            for (int e = 0; e < kMc; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int sp = 0; sp < p.splits; ++sp) {
-                float4 v[kMc];
+            for (int e = 0; e < kMc; ++e) {
+                const long long i = i0 + e * tstride;
+                v0[e] = i < hi ? ldr(mc_in + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < kMc; ++e) {
+                const long long i = i0 + e * tstride;
+                v1[e] = (p.splits > 1 && i < hi) ? ldr(mc_in + stride4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < kMc; ++e) { v0[e].x += v1[e].x; v0[e].y += v1[e].y; v0[e].z += v1[e].z; v0[e].w += v1[e].w; }
+            for (int sp = 2; sp < p.splits; ++sp) {             // more than two splits (not used by the Python layer)
 #pragma unroll
                 for (int e = 0; e < kMc; ++e) {
                     const long long i = i0 + e * tstride;
-                    v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i < hi)
-                        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(v[e].x), "=f"(v[e].y), "=f"(v[e].z), "=f"(v[e].w) : "l"(mc_in + (long long)sp * stride4 + i) : "memory");
+                    if (i < hi) { const float4 t = ldr(mc_in + (long long)sp * stride4 + i); v0[e].x += t.x; v0[e].y += t.y; v0[e].z += t.z; v0[e].w += t.w; }
                 }
-#pragma unroll
-                for (int e = 0; e < kMc; ++e) { acc[e].x += v[e].x; acc[e].y += v[e].y; acc[e].z += v[e].z; acc[e].w += v[e].w; }
             }
 #pragma unroll
             for (int e = 0; e < kMc; ++e) {
                 const long long i = i0 + e * tstride;
                 if (i < hi)
                     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                                 :: "l"(mc_o + i), "f"(acc[e].x * gs), "f"(acc[e].y * gs), "f"(acc[e].z * gs), "f"(acc[e].w * gs) : "memory");
+                                 :: "l"(mc_o + i), "f"(v0[e].x * gs), "f"(v0[e].y * gs), "f"(v0[e].z * gs), "f"(v0[e].w * gs) : "memory");
             }
         }
     } else

@@ -239,9 +239,9 @@ class ShardedHeadPlan:
             self.peer = PeerGradAllReduce.from_symmetric_memory(B, K, C, variant, group=group, max_ctas=sm_reserve or 16, device=dev,
                                                                 multicast=multicast, **plan_kwargs)
             if sm_reserve is None:
-                # summed inside the NVSwitch the all-reduce moves 1/world of the bytes: 8 CTAs keep up with dX; with peer
-                # loads it is paced by NVLink round trips and takes 16
-                sm_reserve = 8 if self.peer.mc_partials is not None else 16
+                # either way the all-reduce is paced by round trips over NVLink (the switch answers a multimem.ld_reduce
+                # in a few microseconds): throughput = bytes in flight, 128 KB per CTA
+                sm_reserve = 16
                 self.peer.max_ctas = sm_reserve
             self.plan = self.peer.plan
             self.flat = self.plan.flat

@@ -20,6 +20,7 @@ if variant == "garbage":
     kw = dict(class_weights=torch.ones(C, device=dev), last_valid_class=-1)
 else:
     y = torch.tensor(synth.make_labels(B, C, 1 / 3, seed=rank), device=dev); kw = {}
+kw["precision"] = os.environ.get("OSB_PRECISION", "fast" if C > 256 else "exact")
 
 import time
 host_us = {}
