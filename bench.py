@@ -254,7 +254,7 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     run_step = eager_step
     if not args.eager and (world == 1 or sp.peer is not None):
         graphs = [(plan.capture(xs[i], w, ys[i]) if world == 1 else sp.capture(xs[i], w, ys[i])) for i in range(nbuf)]
-        launch_mode = "CUDA-graph replay of the whole step" + (" incl. the peer-memory all-reduce" if world > 1 else " (5 kernels)")
+        launch_mode = "CUDA-graph replay of the whole step" + (" incl. the peer-memory all-reduce" if world > 1 else f" ({plan.launches_per_step} kernels)")
 
         def run_step(i):
             graphs[i % nbuf].replay()
@@ -332,7 +332,8 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     k_fwd = statistics.median(e[0].elapsed_time(e[1]) for e in evs) * 1e3
     k_dw = statistics.median(e[1].elapsed_time(e[2]) for e in evs) * 1e3
     k_dx = statistics.median(e[2].elapsed_time(e[3]) for e in evs) * 1e3
-    dw_name = "head_dw2_kernel" + ("+dw_reduce_kernel" if (world == 1 or sp.peer is None) else " (partials; the reduce is the all-reduce)")
+    dw_name = "head_dw2_kernel" + ((" (direct: split 1 adds at the destination)" if plan.dw_direct else "+dw_reduce_kernel")
+                                   if (world == 1 or sp.peer is None) else " (partials; the reduce is the all-reduce)")
     kernels = {fwd_name: k_fwd, dw_name: k_dw, "head_dx2_kernel": k_dx}
     dom = max(kernels, key=kernels.get)
     clocks_k = clk_k.summary()

@@ -146,6 +146,10 @@ int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, const double*
                       void* ws, size_t ws_bytes, void* stream);
 /* 1 when osb_head_forward runs this shape as the split-K cluster kernel (small batches, C <= 256), else 0 */
 int osb_head_forward_is_splitk(int64_t B, int K, int C);
+/* 1 when osb_head_backward writes dW straight from the GEMM (at most two batch splits: the first stores, the second adds
+ * at the destination with a TMA reduce), 0 when split-K partials are summed by a separate fixed-order reduce kernel.
+ * Both are deterministic; the answer only changes the launch count of a step. */
+int osb_head_dw_is_direct(int64_t B, int K, int C);
 
 /* ---- multi-GPU: all-reduce of dW over NVLink peer memory, fused with the split-K reduction ----- *
  * The reference has no collective at all (script/train_all.py:96-118 runs independent jobs); this is what a

@@ -38,6 +38,7 @@ SIGNATURES = {
                               _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
     "osb_head_backward": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _i, _p, _p, _i, _p, _sz, _p]),
     "osb_head_forward_is_splitk": (_i, [_i64, _i, _i]),
+    "osb_head_dw_is_direct": (_i, [_i64, _i, _i]),
     "osb_head_dw_partials_offset": (_sz, []),
     "osb_head_dw_splits": (_i, [_i64, _i, _i]),
     "osb_head_backward_dw_partials": (_i, [_p, _i64, _i, _p, _i64, _i64, _i, _i, _p, _i, _p, _sz, _p]),

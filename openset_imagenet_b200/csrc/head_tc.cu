@@ -44,7 +44,10 @@ constexpr size_t kXchStatBytes = (size_t)kMaxXid * 2 * 4 * 128 * 6 * sizeof(uint
 constexpr size_t kWsOffEpoch = 64;
 constexpr size_t kWsOffPartials = kHeadTicketBytes;
 constexpr size_t kWsOffStats = kWsOffPartials + sizeof(double) * kMaxPartials;
-constexpr size_t kWsOffDw = (kWsOffStats + kXchStatBytes + 255) / 256 * 256;
+// [dW tile flags]: one word per (output tile, CTA of the pair, epilogue warp): "split 0 has stored these rows" (direct dW)
+constexpr int kMaxDwFlagTiles = 1024;
+constexpr size_t kWsOffDwFlags = (kWsOffStats + kXchStatBytes + 255) / 256 * 256;
+constexpr size_t kWsOffDw = kWsOffDwFlags + sizeof(unsigned int) * kMaxDwFlagTiles * 8;
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -969,7 +972,9 @@ static_assert(kDw2SmemBytes <= 232448, "dw2 kernel shared memory");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ CUtensorMap tm_part, int B, int K, int C, int planes, int splits, long long* trace) {
+                const __grid_constant__ CUtensorMap tm_part, const __grid_constant__ CUtensorMap tm_dw,
+                int B, int K, int C, int planes, int splits, int direct, const float* __restrict__ gscale,
+                const double* __restrict__ den, unsigned int* __restrict__ tile_flags, long long* trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2OffBars);
@@ -982,7 +987,7 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         for (int i = 0; i < kDw2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(t_full, 1);
         fence_barrier_init();
-        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_part);
+        prefetch_tensormap(&tm_dz); prefetch_tensormap(&tm_x); prefetch_tensormap(direct ? &tm_dw : &tm_part);
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 256);
     tc_fence_before_sync();
@@ -1044,6 +1049,10 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         // the classes >= C (direct stores put one 16-byte piece per class row and instruction: 5.2 us per CTA, measured).
         uint8_t* my_stage = smem + q * (8 * kStageWarpBytes);
         const uint32_t t_row = tmem_addr(tbase, q * 32, 0);
+        // direct mode (at most two splits): the scaled tile goes straight into dW -- split 0 stores, split 1 ADDS at the
+        // destination (TMA reduce) once split 0's rows have landed; a + b is the same whichever order the hardware took,
+        // so the result is as deterministic as the separate fixed-order reduce kernel it replaces, one pass over dW cheaper
+        const float gs = direct ? (float)((gscale ? (double)gscale[0] : 1.0) / den[0]) : 1.f;
 #pragma unroll 1
         for (int g = 0; g < kDwBN / 32; g += 2) {
             uint32_t v[2][32];
@@ -1055,18 +1064,47 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
                 uint8_t* sbuf = my_stage + (g + h) * kStageWarpBytes;
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                        make_uint4(v[h][4 * c], v[h][4 * c + 1], v[h][4 * c + 2], v[h][4 * c + 3]);
+                    *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                        make_float4(gs * __uint_as_float(v[h][4 * c]), gs * __uint_as_float(v[h][4 * c + 1]),
+                                    gs * __uint_as_float(v[h][4 * c + 2]), gs * __uint_as_float(v[h][4 * c + 3]));
             }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
+            const int row0 = mt * 256 + rank * 128 + q * 32;
+            if (!direct) {
 #pragma unroll
-            for (int g = 0; g < kDwBN / 32; ++g)
-                tma_store_3d(&tm_part, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, mt * 256 + rank * 128 + q * 32, sp);
-            tma_store_commit();
-            tma_store_wait_read<0>();
+                for (int g = 0; g < kDwBN / 32; ++g)
+                    tma_store_3d(&tm_part, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, row0, sp);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+            } else {
+                unsigned int* flag = tile_flags + ((size_t)tile * 2 + rank) * 4 + q;
+                if (sp == 0) {
+#pragma unroll
+                    for (int g = 0; g < kDwBN / 32; ++g)
+                        tma_store_2d(&tm_dw, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, row0);
+                    tma_store_commit();
+                    if (splits > 1) {
+                        tma_store_wait<0>();                      // the rows are in global memory, not merely read out of shared
+                        __threadfence();
+                        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(1u) : "memory");
+                    } else {
+                        tma_store_wait_read<0>();
+                    }
+                } else {
+                    unsigned int f;
+                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory"); } while (f == 0u);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll
+                    for (int g = 0; g < kDwBN / 32; ++g)
+                        tma_reduce_add_2d(&tm_dw, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, row0);
+                    tma_store_commit();
+                    *flag = 0u;                                   // consumed: the workspace is left reusable
+                    tma_store_wait_read<0>();
+                }
+            }
         }
         __syncwarp();
     }
@@ -1670,8 +1708,11 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
 }
 
 // the dW GEMM (split-K partials into the workspace); returns the split count through *splits_out
+// direct_dw != NULL (pair kernel, at most two splits): the scaled result goes straight into dW, no partials, no reduce kernel;
+// *direct_out says whether that happened
 static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, int64_t ldx, int64_t B, int K, int C,
-                       void* ws, cudaStream_t st, int* splits_out) {
+                       void* ws, cudaStream_t st, int* splits_out, float* direct_dw = nullptr, const float* gscale = nullptr,
+                       const double* den = nullptr, bool* direct_out = nullptr) {
     CUtensorMap tdz, tx;
     OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, 64), "dz (MN-major)");
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
@@ -1683,11 +1724,19 @@ static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, 
     if (dw_pairs(C)) {
         rc = set_smem(head_dw2_kernel, kDw2SmemBytes);
         if (rc) return rc;
-        const int units = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN) * splits;
-        CUtensorMap tpart;
+        const int tiles = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN);
+        const int units = tiles * splits;
+        static const bool no_direct = getenv("OSB_NO_DIRECT_DW") != nullptr;          // developer A/B switch
+        const bool direct = direct_dw != nullptr && splits <= 2 && tiles <= kMaxDwFlagTiles && !no_direct;
+        if (direct_out) *direct_out = direct;
+        CUtensorMap tpart, tdw;
         OSB_TMAP(make_tmap_f32_3d(&tpart, partials, (uint64_t)splits, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW partials (store)");
+        tdw = tpart;
+        if (direct) OSB_TMAP(make_tmap_f32_2d(&tdw, direct_dw, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW (direct store / reduce)");
+        unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffDwFlags);
         cudaLaunchConfig_t cfg = pdl_config(dim3(units * 2), dim3(kThreads), kDw2SmemBytes, st, &pdl_attr);
-        OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, (int)B, K, C, planes, splits, g_trace));
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, tdw, (int)B, K, C, planes, splits, direct ? 1 : 0, gscale, den,
+                                    flags, g_trace));
     } else {
         rc = set_smem(head_dw_kernel, kDwSmemBytes);
         if (rc) return rc;
@@ -1749,8 +1798,10 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
     }
     if (dw) {
         int splits = 1;
-        rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits);
+        bool direct = false;
+        rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits, dw, gscale, den, &direct);
         if (rc) return rc;
+      if (!direct) {
         const float* partials = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + kWsOffDw);
         const size_t n4 = (size_t)C * K / 4;
         int rgrid = (int)((n4 + 255) / 256);
@@ -1760,6 +1811,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
         cudaLaunchConfig_t cfg = pdl_config(dim3(rgrid), dim3(256), 0, st, &pdl_attr);
         OSB_CUDA(cudaLaunchKernelEx(&cfg, dw_reduce_kernel, reinterpret_cast<const float4*>(partials), splits, n4, gscale, den,
                                     reinterpret_cast<float4*>(dw)));
+      }
     }
     if (db) {
         db_kernel<<<(C + 63) / 64, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dz), lddz, (int)B, C, dz_planes, gscale, den, db);
@@ -1770,6 +1822,12 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
 
 // ---- multi-GPU: the dW GEMM alone (split-K partials stay in the workspace), for the peer-memory all-reduce ----
 extern "C" size_t osb_head_dw_partials_offset(void) { return kWsOffDw; }
+extern "C" int osb_head_dw_is_direct(int64_t B, int K, int C) {
+    if (osb::check_device() != OSB_OK || !dw_pairs(C)) return 0;
+    static const bool no_direct = getenv("OSB_NO_DIRECT_DW") != nullptr;
+    const int tiles = ((C + 255) / 256) * ((K + kDwBN - 1) / kDwBN);
+    return (dw_splits((int)B, K, C) <= 2 && tiles <= kMaxDwFlagTiles && !no_direct) ? 1 : 0;
+}
 extern "C" int osb_head_dw_splits(int64_t B, int K, int C) { return dw_splits((int)B, K, C); }
 extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
                                              int64_t B, int K, int C, float* db_partial, int local_reduce,

@@ -260,7 +260,9 @@ class ShardedHeadPlan:
         self._abranch = torch.cuda.Stream(device=dev)
         # our kernels per step: label statistics, forward, dW GEMM, dX, and the split-K reduce (NCCL path) or the peer
         # all-reduce that replaces it (+ the denominator's peer sum for softmax / garbage, + db with a bias)
-        self.launches_per_step = 5 + (1 if bias else 0) + (1 if (self.peer is not None and not self.entropic) else 0)
+        self.launches_per_step = ((5 if self.peer is not None else self.plan.launches_per_step - (1 if bias else 0)) + (1 if bias else 0)
+                                  + (1 if (self.peer is not None and not self.entropic) else 0)
+                                  + (1 if (self.peer is not None and self.peer.local_reduce) else 0))
 
     # ---- one step; every call below only ENQUEUES, so the same body runs eagerly or under stream capture ----
     def _body(self, x, w, y, bias=None, marks=None):

@@ -90,7 +90,9 @@ class HeadPlan:
         self.dx = torch.empty(B, K, dtype=dx_dtype, device=d)
         self.dw = self.flat[:C * K].view(C, K)
         self.db = self.flat[C * K:C * K + C] if bias else None
-        self.launches_per_step = 5 + (1 if bias else 0)   # label_stats, fwd, dx, dw, dw-reduce (+ db)
+        self.dw_direct = bool(L.size("osb_head_dw_is_direct", B, K, C))
+        # label_stats, fwd, dx, dw (+ the split-K reduce unless the GEMM writes dW directly) (+ db)
+        self.launches_per_step = 4 + (0 if self.dw_direct else 1) + (1 if bias else 0)
 
     @property
     def den_step(self) -> torch.Tensor:
