@@ -692,6 +692,10 @@ def main():
     # Libraries print to stdout (NCCL's version banner does at every debug level above NONE): keep fd 1 for the
     # JSON line alone and send everything else to stderr.
     global _REAL_STDOUT
+    # `kill -USR1 <pid>` (or `timeout -s USR1`) dumps every thread's Python stack to stderr: where a stuck run is waiting
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True, chain=False)
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)

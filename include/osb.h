@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OSB_ABI_VERSION 3
+#define OSB_ABI_VERSION 4
 
 /* status codes */
 #define OSB_OK             0
@@ -53,6 +53,8 @@ extern "C" {
 
 /* osb_head_forward flags */
 #define OSB_FWD_DEN_FROM_PREV_KERNEL 1   /* see osb_head_forward */
+#define OSB_FWD_PUBLISH_ROW_TILES 2      /* see osb_head_forward */
+#define OSB_BWD_DZ_FROM_PREV_FORWARD 1   /* see osb_head_backward */
 
 /* label types accepted by the OSCR row reduce (`gt` is float32 in the reference's npz files,
  * train.py:212, and cast with astype(int) at util.py:100) */
@@ -127,10 +129,22 @@ int osb_loss_from_logits(const void* logits, int dtype, int64_t ld, const int64_
  *           call on `stream` is the one that writes den (osb_label_stats, or osb_peer_sum after it) and that ITS
  *           predecessor has completed the inputs: small batches are then launched with programmatic stream
  *           serialization, run under that kernel, and wait for it only before den is read.
+ *           flags & OSB_FWD_PUBLISH_ROW_TILES: the persistent forward (heads wider than 128 classes, batches the
+ *           split-K kernel does not take) clears a word per (256-row tile, unit, epilogue warp) in the workspace when it
+ *           starts and sets it when that warp's grad-logits of the tile have landed in global memory; it costs nothing
+ *           and is the producer side of OSB_BWD_DZ_FROM_PREV_FORWARD below.
  *           max_ctas > 0 bounds the persistent grids (forward, dX) so that a collective running beside them finds
  *           free SMs; 0 = one CTA per SM.
  * backward: g = gscale[0] (device, NULL = 1) / den[0];  dx (nullable) [B, lddx] of dx_dtype (OSB_BF16 or OSB_F32)
  *           = g * dz @ w ; dw [C, K] float32 = g * dz^T @ x ; db (nullable) [C] float32 = g * column sums of dz.
+ *           flags & OSB_BWD_DZ_FROM_PREV_FORWARD (dw without dx, and osb_head_backward_dw_partials): the caller promises
+ *           that the kernel directly in front of this call on `stream` is osb_head_forward with
+ *           OSB_FWD_PUBLISH_ROW_TILES on the same B, K, C, dz and workspace.  The dW GEMM then does not wait for that
+ *           kernel to finish: its first CTA pairs become resident on the SMs the forward leaves idle (64 of 74 SM pairs
+ *           work at 16384 x 2048 -> 1000) and consume the rows of dz tile by tile as they are published.  The result is
+ *           the same bits; a caller that breaks the promise gets the plain dependency back after a 0.5 s time-out.
+ *           Opt-in: at that shape the chip is power-limited under a full load, and the overlap measured 5 % SLOWER than
+ *           the plain launch order; it is kept for shapes and power budgets where idle SMs are free.
  */
 size_t osb_head_workspace_bytes(int64_t B, int K, int C);
 int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
@@ -142,7 +156,7 @@ int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bia
                      void* ws, size_t ws_bytes, void* stream);
 int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, const double* den, const void* x, int64_t ldx,
                       const void* w, int64_t B, int K, int C, const float* gscale,
-                      void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas,
+                      void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas, int flags,
                       void* ws, size_t ws_bytes, void* stream);
 /* 1 when osb_head_forward runs this shape as the split-K cluster kernel (small batches, C <= 256), else 0 */
 int osb_head_forward_is_splitk(int64_t B, int K, int C);
@@ -177,7 +191,7 @@ int osb_head_dw_is_direct(int64_t B, int K, int C);
 size_t osb_head_dw_partials_offset(void);
 int osb_head_dw_splits(int64_t B, int K, int C);
 int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
-                                  int64_t B, int K, int C, float* db_partial, int local_reduce,
+                                  int64_t B, int K, int C, float* db_partial, int local_reduce, int flags,
                                   void* ws, size_t ws_bytes, void* stream);
 size_t osb_head_dw_allreduce_flag_bytes(int world);
 int osb_head_dw_allreduce(const void* const* peer_partials, void* const* peer_dw, const void* const* peer_extra,

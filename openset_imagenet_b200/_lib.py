@@ -14,12 +14,14 @@ import torch
 
 from . import _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, ERR_ARG, ERR_SHAPE, ERR_WORKSPACE, ERR_CUDA, ERR_ARCH = 0, -1, -2, -3, -4, -5
 ENTROPIC, SOFTMAX, GARBAGE = 0, 1, 2
 F32, BF16 = 0, 1
 LABEL_I64, LABEL_F32, LABEL_I32 = 0, 1, 2
 FWD_DEN_FROM_PREV_KERNEL = 1
+FWD_PUBLISH_ROW_TILES = 2
+BWD_DZ_FROM_PREV_FORWARD = 1
 
 _p, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 
@@ -36,12 +38,12 @@ SIGNATURES = {
     "osb_head_workspace_bytes": (_sz, [_i64, _i, _i]),
     "osb_head_forward": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _i64, _p, _i,
                               _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
-    "osb_head_backward": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _i, _p, _p, _i, _p, _sz, _p]),
+    "osb_head_backward": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _sz, _p]),
     "osb_head_forward_is_splitk": (_i, [_i64, _i, _i]),
     "osb_head_dw_is_direct": (_i, [_i64, _i, _i]),
     "osb_head_dw_partials_offset": (_sz, []),
     "osb_head_dw_splits": (_i, [_i64, _i, _i]),
-    "osb_head_backward_dw_partials": (_i, [_p, _i64, _i, _p, _i64, _i64, _i, _i, _p, _i, _p, _sz, _p]),
+    "osb_head_backward_dw_partials": (_i, [_p, _i64, _i, _p, _i64, _i64, _i, _i, _p, _i, _i, _p, _sz, _p]),
     "osb_head_dw_allreduce_flag_bytes": (_sz, [_i]),
     "osb_head_dw_allreduce": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _i64, _p, _i, _i, _p, _p, _p, _p, _i, _p]),
     "osb_head_dw_allreduce_error": (_i, [_p, _i, _p]),

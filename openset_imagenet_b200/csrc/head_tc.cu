@@ -47,7 +47,13 @@ constexpr size_t kWsOffStats = kWsOffPartials + sizeof(double) * kMaxPartials;
 // [dW tile flags]: one word per (output tile, CTA of the pair, epilogue warp): "split 0 has stored these rows" (direct dW)
 constexpr int kMaxDwFlagTiles = 1024;
 constexpr size_t kWsOffDwFlags = (kWsOffStats + kXchStatBytes + 255) / 256 * 256;
-constexpr size_t kWsOffDw = kWsOffDwFlags + sizeof(unsigned int) * kMaxDwFlagTiles * 8;
+// [row-tile flags]: 8 slots (unit of the group x CTA of the pair) x 8 epilogue warps per 256-row tile of the batch: "this
+// warp's grad-logits of the tile have landed" -- lets the dW GEMM behind a forward start on the SMs the forward leaves idle
+constexpr int kMaxRowFlagTiles = 1024;
+constexpr int kRowFlagWords = 64;
+constexpr int kRowFlagTileRows = 256;
+constexpr size_t kWsOffRowFlags = kWsOffDwFlags + sizeof(unsigned int) * kMaxDwFlagTiles * 8;
+constexpr size_t kWsOffDw = kWsOffRowFlags + sizeof(unsigned int) * kMaxRowFlagTiles * kRowFlagWords;
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -141,6 +147,7 @@ struct FwdArgs {
     double* partials; unsigned int* ticket;
     uint2* xch_stats;          // [row block][2][CL][128][6] (value, epoch) words: per-row statistics exchanged between the units of a group
     unsigned int* xch_epoch;   // epochs used so far on this workspace; only grows, so stale words never match
+    unsigned int* tile_flags;  // nullable: [row tile][unit * 2 + cta][epilogue warp] "grad-logits landed" words (OSB_FWD_PUBLISH_ROW_TILES)
     long long* trace;      // optional [gridDim.x][64] clock stamps (developer tool, NULL in production)
 };
 
@@ -260,6 +267,12 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
     for (int i = threadIdx.x; i < 2 * BM * 8; i += Cfg::kThreads) sX[i] = make_uint2(0u, 0u);     // epoch 0 = nothing published
     if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
+    if (PAIR && a.tile_flags && warp >= kEpiWarp0 && lane == 0) {
+        // every word is cleared by the thread that sets it later, and before this CTA lets the dependent kernel start
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters)
+            a.tile_flags[(size_t)tile * kRowFlagWords + (rank * 2 + cr) * 8 + (warp - kEpiWarp0)] = 0u;
+        __threadfence();
+    }
     tc_fence_before_sync();
     if (PAIR) cluster_sync_(); else __syncthreads();
     tc_fence_after_sync();
@@ -352,6 +365,16 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int c_base = h * G * 32;                      // this warp's columns: [c_base, c_base + G * 32) of the unit's BN
         uint8_t* my_stage = sDz + (warp - kEpiWarp0) * 2 * kStageWarpBytes;
         uint32_t n_stores = 0;
+        int pub_tile = -1;                                   // tile whose grad-logits are stored but not yet published
+        auto publish = [&]() {
+            if (PAIR && a.tile_flags && pub_tile >= 0 && lane == 0) {
+                tma_store_wait<0>();                         // in global memory, not merely read out of shared memory
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;"
+                             :: "l"(a.tile_flags + (size_t)pub_tile * kRowFlagWords + (rank * 2 + cr) * 8 + (warp - kEpiWarp0)), "r"(1u) : "memory");
+            }
+            pub_tile = -1;
+        };
         const uint32_t ep_base = (CL > 1) ? *a.xch_epoch : 0u;
         double loss_acc = 0.0;
         uint32_t it = 0;
@@ -521,6 +544,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // (a thread owns a row, so direct stores would scatter 16-byte pieces over 32 rows per instruction; the TMA
             // store writes whole 128-byte lines and clips the columns >= C and the rows >= B itself)
             if (a.write_dz) {
+                // Row-tile hand-over: the PREVIOUS tile's stores were issued a whole tile ago and have long landed in global
+                // memory (waiting for them costs nothing here; waiting right behind the stores would stall the warp for
+                // their full latency): publish that tile to the dW GEMM that may already run on the SMs this grid leaves idle
+                publish();
                 const bool live = (rm.mode == kRowOneHot || rm.mode == kRowUniform);
                 const float coef = live ? rm.omega / s : 0.f;
                 const float coef_e = coef * fast_exp2((m_slice - m) * kLog2e);   // e was taken relative to the slice max
@@ -573,6 +600,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         if (PLANES2) emit(std::true_type{});
                     }
                 }
+                pub_tile = tile;
             }
             if (tr && blockIdx.x == 0) a.trace[256 * 64 + 128 + it * 8 + 3] = gtime();
             // ---- per-row outputs (unit 0 of the group): loss, p[target], max p over the valid columns, max p, arg-max ----
@@ -653,6 +681,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 }
             }
         }
+        publish();                                        // the last tile of this CTA (after the loss reduction: this one does wait)
         if (lane == 0) tma_store_wait_read<0>();          // the staging buffers have been read; the data lands before the grid ends
         if (trx) a.trace[256 * 64 + 192 + 1] = gtime();
     }
@@ -974,7 +1003,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_part, const __grid_constant__ CUtensorMap tm_dw,
                 int B, int K, int C, int planes, int splits, int direct, const float* __restrict__ gscale,
-                const double* __restrict__ den, unsigned int* __restrict__ tile_flags, long long* trace) {
+                const double* __restrict__ den, unsigned int* __restrict__ tile_flags,
+                const unsigned int* row_flags, int row_flag_slots, long long* trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDw2OffBars);
@@ -993,12 +1023,16 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     tc_fence_before_sync();
     cluster_sync_();
     tc_fence_after_sync();
-    pdl_wait();                 // dZ comes from the forward kernel in front of this one
+    // dZ comes from the forward kernel in front of this one: wait for all of it -- or (row_flags) run under it on the SMs it
+    // leaves idle and take the rows of dZ as the forward publishes them, 256-row tile by tile
+    if (!row_flags) pdl_wait();
     pdl_trigger();              // the split-K reduce behind it may be scheduled
     const uint32_t tbase = *tmem_slot;
     const int n_tiles = (K + kDwBN - 1) / kDwBN;
     const int unit = blockIdx.x >> 1;
-    const int sp = unit % splits, tile = unit / splits;
+    // split-major: the first CTA pairs (the ones that become resident first) take the first rows of the batch
+    const int tiles_all = ((C + 255) / 256) * n_tiles;
+    const int sp = unit / tiles_all, tile = unit % tiles_all;
     const int mt = tile / n_tiles, nt = tile % n_tiles;
     const int kb_rows = (B + BK - 1) / BK, kb_total = kb_rows * planes;     // batch rows of every dZ plane
     const int kb0 = (int)((int64_t)kb_total * sp / splits), kb1 = (int)((int64_t)kb_total * (sp + 1) / splits);
@@ -1006,11 +1040,47 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     // warps 0 and 1 run their issue loops converged, one elected lane issues (see head_fwd_kernel)
     if (warp == 0) {
         uint32_t it = 0;
+        int ready_lo = 0, ready_hi = 0;                     // row tiles [ready_lo, ready_hi) of dZ are known to have landed
+        const int n_row_tiles = (B + kRowFlagTileRows - 1) / kRowFlagTileRows;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const uint32_t s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
+            const int pl = kb >= kb_rows ? 1 : 0, kr = kb - pl * kb_rows;
+            if (row_flags) {
+                const int rt = (kr * BK) / kRowFlagTileRows;
+                if (rt < ready_lo || rt >= ready_hi) {
+                    // lanes 8j .. 8j+7 look at the (up to) 8 slots x 8 warp words of row tile rt + j: four tiles per poll
+                    const int j = rt + (lane >> 3), slot = lane & 7;
+                    const bool mine = j < n_row_tiles && slot < row_flag_slots;
+                    const unsigned int* fp = row_flags + ((size_t)j * 8 + slot) * 8;
+                    const long long t0 = gtime();
+                    unsigned got;
+                    for (;;) {
+                        bool ok = true;
+                        if (mine) {
+                            uint32_t f[8];
+                            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]) : "l"(fp) : "memory");
+                            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]) : "l"(fp + 4) : "memory");
+                            ok = (f[0] & f[1] & f[2] & f[3] & f[4] & f[5] & f[6] & f[7]) != 0u;
+                        }
+                        got = __ballot_sync(0xffffffffu, ok);
+                        if ((got & 0xffu) == 0xffu) break;
+                        if (__any_sync(0xffffffffu, gtime() - t0 > 500000000LL)) {   // not behind a publishing forward after all: plain dependency
+                            pdl_wait();
+                            got = 0xffffffffu; ready_lo = -(1 << 30);
+                            break;
+                        }
+                        __nanosleep(256);
+                    }
+                    __threadfence();                            // acquire side of the flags' release
+                    asm volatile("fence.proxy.async;" ::: "memory");    // the loads that follow are TMA (async proxy) reads
+                    int n = 1;
+                    while (n < 4 && ((got >> (8 * n)) & 0xffu) == 0xffu) ++n;
+                    if (ready_lo < 0) { ready_lo = 0; ready_hi = 1 << 30; }
+                    else { ready_lo = rt; ready_hi = rt + n; }
+                }
+            }
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + s * kDw2StageBytes;
-            const int pl = kb >= kb_rows ? 1 : 0, kr = kb - pl * kb_rows;
             if (elect_one()) {
                 if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDw2StageBytes);     // both CTAs' bytes land on the leader's barrier
 #pragma unroll
@@ -1043,6 +1113,7 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         const int q = warp & 3;
         mbar_wait_warp(t_full, 0);
         tc_fence_after_sync();
+        if (row_flags) pdl_wait();      // den may come from the kernels in front; by now they are done or nearly so
         if (trace && threadIdx.x == kEpiWarp0 * 32) trace[blockIdx.x * 8 + 1] = gtime();
         // Every MMA has completed, so the operand stages are free: the warp stages its 32 classes x 256 features (fp32) there
         // as eight 128B-swizzled boxes and hands them to TMA stores, which write whole lines of the partial matrix and clip
@@ -1592,6 +1663,13 @@ extern "C" int osb_head_forward_is_splitk(int64_t B, int K, int C) {
     if (osb::check_device() != OSB_OK) return 0;
     return fwd_use_splitk(B, K, C, 0) ? 1 : 0;
 }
+// Row-tile hand-over between the persistent forward and the dW GEMM behind it (OSB_FWD_PUBLISH_ROW_TILES /
+// OSB_BWD_DZ_FROM_PREV_FORWARD): both sides decide from the shape alone.  A forward that is bounded by max_ctas may run
+// as the persistent kernel where this says split-K; it then publishes nothing and the backward does not ask (safe side).
+static bool row_flags_usable(int64_t B, int K, int C) {
+    static const bool off = getenv("OSB_NO_ROW_FLAGS") != nullptr;               // developer A/B switch
+    return !off && C > BM && !fwd_use_splitk(B, K, C, 0) && (B + kRowFlagTileRows - 1) / kRowFlagTileRows <= kMaxRowFlagTiles;
+}
 static long long* g_trace = nullptr;
 static int g_dbg = 0;
 extern "C" void osb_debug_set_head_dbg(int v) { g_dbg = v; }
@@ -1649,7 +1727,8 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     OSB_REQUIRE(valid_cols >= 1 && valid_cols <= C, OSB_ERR_ARG, "osb_head_forward: valid_cols=%d outside [1,%d]", valid_cols, C);
     OSB_REQUIRE(!dz || (lddz >= C && lddz % 8 == 0), OSB_ERR_ARG, "osb_head_forward: lddz=%lld must be >= C and a multiple of 8", (long long)lddz);
     OSB_REQUIRE(!dz || dz_planes == 1 || dz_planes == 2, OSB_ERR_ARG, "osb_head_forward: dz_planes=%d must be 1 or 2", dz_planes);
-    OSB_REQUIRE(max_ctas >= 0 && (flags & ~OSB_FWD_DEN_FROM_PREV_KERNEL) == 0, OSB_ERR_ARG, "osb_head_forward: bad flags / max_ctas");
+    OSB_REQUIRE(max_ctas >= 0 && (flags & ~(OSB_FWD_DEN_FROM_PREV_KERNEL | OSB_FWD_PUBLISH_ROW_TILES)) == 0, OSB_ERR_ARG,
+                "osb_head_forward: bad flags / max_ctas");
     OSB_REQUIRE(!(flags & OSB_FWD_DEN_FROM_PREV_KERNEL) || den, OSB_ERR_ARG, "osb_head_forward: OSB_FWD_DEN_FROM_PREV_KERNEL without den");
     OSB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)dz % 16 == 0), OSB_ERR_ARG,
                 "osb_head_forward: x, w and dz must be 16-byte aligned");
@@ -1676,6 +1755,8 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.xch_epoch = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffEpoch);
     a.xch_stats = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + kWsOffStats);
     a.trace = g_trace;
+    a.tile_flags = ((flags & OSB_FWD_PUBLISH_ROW_TILES) && dz && row_flags_usable(B, K, C))
+                       ? reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffRowFlags) : nullptr;
     if (splitk) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)((B + BM - 1) / BM) * kSkS);
@@ -1711,8 +1792,8 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
 // direct_dw != NULL (pair kernel, at most two splits): the scaled result goes straight into dW, no partials, no reduce kernel;
 // *direct_out says whether that happened
 static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, int64_t ldx, int64_t B, int K, int C,
-                       void* ws, cudaStream_t st, int* splits_out, float* direct_dw = nullptr, const float* gscale = nullptr,
-                       const double* den = nullptr, bool* direct_out = nullptr) {
+                       void* ws, cudaStream_t st, int* splits_out, bool row_flags, float* direct_dw = nullptr,
+                       const float* gscale = nullptr, const double* den = nullptr, bool* direct_out = nullptr) {
     CUtensorMap tdz, tx;
     OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, 64), "dz (MN-major)");
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
@@ -1735,8 +1816,11 @@ static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, 
         if (direct) OSB_TMAP(make_tmap_f32_2d(&tdw, direct_dw, (uint64_t)C, (uint64_t)K, (uint64_t)K, 32), "dW (direct store / reduce)");
         unsigned int* flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffDwFlags);
         cudaLaunchConfig_t cfg = pdl_config(dim3(units * 2), dim3(kThreads), kDw2SmemBytes, st, &pdl_attr);
+        // the forward's units: ceil(C / 256) class slices x 2 CTAs publish one word per epilogue warp and row tile
+        const unsigned int* rflags = (row_flags && row_flags_usable(B, K, C))
+                                         ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(ws) + kWsOffRowFlags) : nullptr;
         OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, tdw, (int)B, K, C, planes, splits, direct ? 1 : 0, gscale, den,
-                                    flags, g_trace));
+                                    flags, rflags, ((C + 255) / 256) * 2, g_trace));
     } else {
         rc = set_smem(head_dw_kernel, kDwSmemBytes);
         if (rc) return rc;
@@ -1762,13 +1846,14 @@ static int check_backward_args(const char* fn, const void* dz, int64_t lddz, int
 
 extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, const double* den, const void* x, int64_t ldx,
                                  const void* w, int64_t B, int K, int C, const float* gscale,
-                                 void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas,
+                                 void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas, int flags,
                                  void* ws, size_t ws_bytes, void* stream) {
     OSB_ENTRY_GUARD();
     int rc = check_backward_args("osb_head_backward", dz, lddz, dz_planes, x, ldx, B, K, C, ws, ws_bytes);
     if (rc) return rc;
     OSB_REQUIRE(den, OSB_ERR_ARG, "osb_head_backward: null den");
     OSB_REQUIRE(!dx || w, OSB_ERR_ARG, "osb_head_backward: dx needs w");
+    OSB_REQUIRE((flags & ~OSB_BWD_DZ_FROM_PREV_FORWARD) == 0, OSB_ERR_ARG, "osb_head_backward: bad flags %d", flags);
     OSB_REQUIRE(dx_dtype == OSB_BF16 || dx_dtype == OSB_F32, OSB_ERR_ARG, "osb_head_backward: bad dx_dtype %d", dx_dtype);
     OSB_REQUIRE(!dx || (lddx >= K && lddx % 8 == 0), OSB_ERR_ARG, "osb_head_backward: bad lddx=%lld", (long long)lddx);
     OSB_REQUIRE(((uintptr_t)w % 16 == 0) && ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0) && max_ctas >= 0, OSB_ERR_ARG,
@@ -1799,7 +1884,9 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
     if (dw) {
         int splits = 1;
         bool direct = false;
-        rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits, dw, gscale, den, &direct);
+        // the dW GEMM is directly behind the forward only when this call launches no dX in front of it
+        rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits, (flags & OSB_BWD_DZ_FROM_PREV_FORWARD) && !dx,
+                         dw, gscale, den, &direct);
         if (rc) return rc;
       if (!direct) {
         const float* partials = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + kWsOffDw);
@@ -1830,14 +1917,15 @@ extern "C" int osb_head_dw_is_direct(int64_t B, int K, int C) {
 }
 extern "C" int osb_head_dw_splits(int64_t B, int K, int C) { return dw_splits((int)B, K, C); }
 extern "C" int osb_head_backward_dw_partials(const void* dz, int64_t lddz, int dz_planes, const void* x, int64_t ldx,
-                                             int64_t B, int K, int C, float* db_partial, int local_reduce,
+                                             int64_t B, int K, int C, float* db_partial, int local_reduce, int flags,
                                              void* ws, size_t ws_bytes, void* stream) {
     OSB_ENTRY_GUARD();
     int rc = check_backward_args("osb_head_backward_dw_partials", dz, lddz, dz_planes, x, ldx, B, K, C, ws, ws_bytes);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     int splits = 1;
-    rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits);
+    OSB_REQUIRE((flags & ~OSB_BWD_DZ_FROM_PREV_FORWARD) == 0, OSB_ERR_ARG, "osb_head_backward_dw_partials: bad flags %d", flags);
+    rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits, (flags & OSB_BWD_DZ_FROM_PREV_FORWARD) != 0);
     if (rc) return rc;
     if (local_reduce && splits > 1) {
         // sum the splits into split 0 in place (every thread reads all splits of its elements before it writes them): the

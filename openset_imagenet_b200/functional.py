@@ -132,21 +132,23 @@ class HeadPlan:
     def backward_dx(self, x, w, gscale=None, den=None, max_ctas=0):
         L.call("osb_head_backward", L.ptr(self.dz), self.lddz, self.planes, L.ptr(self.den_step if den is None else den),
                L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), L.ptr(self.dx), self.K, self._dx_code(),
-               None, None, int(max_ctas), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+               None, None, int(max_ctas), 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def backward_dw(self, x, w, gscale=None, den=None):
+    def backward_dw(self, x, w, gscale=None, den=None, flags=0):
+        """``flags=L.BWD_DZ_FROM_PREV_FORWARD``: this launch is directly behind ``forward(..., flags=L.FWD_PUBLISH_ROW_TILES)``
+        on the stream; the dW GEMM then starts on the SMs the forward leaves idle and takes dZ row tile by row tile."""
         L.call("osb_head_backward", L.ptr(self.dz), self.lddz, self.planes, L.ptr(self.den_step if den is None else den),
                L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), None, self.K, self._dx_code(),
-               L.ptr(self.dw), L.ptr(self.db), 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+               L.ptr(self.dw), L.ptr(self.db), 0, int(flags), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def backward_dw_partials(self, x, local_reduce=False):
+    def backward_dw_partials(self, x, local_reduce=False, flags=0):
         """Only the dW GEMM: un-scaled split-K partials stay in the workspace (input of the peer-memory all-reduce),
         summed into the first one when ``local_reduce``; with a bias the un-scaled column sums of dZ go to the db slots
-        of the packed buffer."""
+        of the packed buffer.  ``flags`` as in ``backward_dw``."""
         L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, self.planes, L.ptr(x), self.K, self.B, self.K, self.C,
-               L.ptr(self.db), 1 if local_reduce else 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+               L.ptr(self.db), 1 if local_reduce else 0, int(flags), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None):
+    def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None, handover=False):
         """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five
         kernels on the CURRENT CONTENTS of those tensors with a single launch call.  The small-batch configurations
         (B <= 1024) are bound by launch latency, not by the kernels, so this is the path to use in a training loop."""
@@ -154,8 +156,14 @@ class HeadPlan:
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         # Small batches leave most SMs idle and every kernel is a few microseconds of latency: dX and dW only depend on
-        # dZ, so they become parallel branches of the graph.  Large batches fill the GPU with either kernel and stay serial.
+        # dZ, so they become parallel branches of the graph.  Large batches fill the GPU with either kernel and stay serial:
+        # under a full load the chip is power-limited (the SM clock falls from 1.85 to 1.58 GHz between 16 and 148 busy
+        # SMs within one launch), so kernels that overlap only share the same budget -- measured at 16384 x 2048 -> 1000,
+        # 12 + 6 interleaved runs on one box: serial 184.9 us, parallel branches 184.8 us, parallel branches with the
+        # row-tile hand-over (``handover=True``: the dW GEMM starts under the forward on the SMs it leaves idle) 194.8 us.
         fork = self.B <= 4096 if parallel_backward is None else bool(parallel_backward)
+        pub = L.FWD_PUBLISH_ROW_TILES if (fork and handover) else 0
+        take = L.BWD_DZ_FROM_PREV_FORWARD if (fork and handover) else 0
         branch = torch.cuda.Stream(device=self.dev) if fork else None
         # Entropic loss: the denominator is a constant, so the label statistics (counts for the caller) are a branch
         # beside the backward kernels instead of the first link of the chain.
@@ -174,9 +182,9 @@ class HeadPlan:
                 # the forward kernel runs under the label statistics it follows and waits for them only before it
                 # divides the loss (OSB_FWD_DEN_FROM_PREV_KERNEL); the grad-logits do not depend on the denominator
                 self.label_stats(y)
-                self.forward(x, w, y, bias, want_pred=False, flags=L.FWD_DEN_FROM_PREV_KERNEL)
+                self.forward(x, w, y, bias, want_pred=False, flags=L.FWD_DEN_FROM_PREV_KERNEL | pub)
             else:
-                self.forward(x, w, y, bias, want_pred=False)
+                self.forward(x, w, y, bias, want_pred=False, flags=pub)
             if fork:
                 if side_labels:
                     labels_beside()
@@ -185,7 +193,7 @@ class HeadPlan:
                 branch.wait_stream(side)
                 with torch.cuda.stream(branch):
                     self.backward_dx(x, w, gscale)
-                self.backward_dw(x, w, gscale)
+                self.backward_dw(x, w, gscale, flags=take)
                 side.wait_stream(branch)
             else:
                 self.backward_dx(x, w, gscale)

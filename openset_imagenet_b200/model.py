@@ -124,7 +124,7 @@ class _FusedHeadFn(torch.autograd.Function):
             dw = torch.empty(Cc, k64, dtype=torch.float32, device=dev) if need_dw else None
             db = torch.empty(Cc, dtype=torch.float32, device=dev) if need_db else None
             L.call("osb_head_backward", L.ptr(dz), lddz, planes, L.ptr(den), L.ptr(x), x.stride(0), L.ptr(w), B, k64, Cc, L.ptr(g),
-                   L.ptr(dx), k64, L.F32 if dx_t == torch.float32 else L.BF16, L.ptr(dw), L.ptr(db), 0,
+                   L.ptr(dx), k64, L.F32 if dx_t == torch.float32 else L.BF16, L.ptr(dw), L.ptr(db), 0, 0,
                    L.ptr(ws), ws.numel(), st)
         if dx is not None:
             dx = dx[:, :K] if k64 != K else dx

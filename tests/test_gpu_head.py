@@ -175,12 +175,17 @@ def test_head_many_tiles_garbage_variant_with_bias():
 
 
 @pytest.mark.parametrize("B,K,C,variant", [(300, 256, 300, "entropic"), (5000, 256, 300, "entropic"),
-                                             (1024, 2048, 152, "entropic"), (1024, 2048, 152, "garbage")])
-def test_head_plan_graph_replay_matches_eager_step(B, K, C, variant):
+                                             (1024, 2048, 152, "entropic"), (1024, 2048, 152, "garbage"),
+                                             (9000, 512, 600, "entropic"), (4100, 256, 1000, "garbage")])
+@pytest.mark.parametrize("handover", [False, True])
+def test_head_plan_graph_replay_matches_eager_step(B, K, C, variant, handover):
     """HeadPlan.capture (dX and dW as parallel graph branches for small batches, serial for large ones; for the entropic
     loss the label statistics as one more branch, with the row count as the forward kernel's denominator) reproduces the
     eager step bit for bit, label counts and denominator included: the kernels are deterministic and the graph only
-    changes how they are launched.  The 1024-row cases take the split-K forward."""
+    changes how they are launched.  ``handover``: parallel branches with the dW GEMM launched programmatically behind the
+    persistent forward and fed row tile by row tile through the workspace flags (OSB_FWD_PUBLISH_ROW_TILES /
+    OSB_BWD_DZ_FROM_PREV_FORWARD).  The 1024-row cases take the split-K forward (no hand-over there), the others the
+    persistent one with 2, 3 and 4 class slices and ragged last row tiles."""
     from openset_imagenet_b200.functional import HeadPlan
     dev = torch.device(DEV)
     g = torch.Generator(device=dev).manual_seed(B)
@@ -198,7 +203,7 @@ def test_head_plan_graph_replay_matches_eager_step(B, K, C, variant):
     plan.step(x, w, y)
     torch.cuda.synchronize()
     ref = [t.clone() for t in outs()]
-    graph = plan.capture(x, w, y)
+    graph = plan.capture(x, w, y, parallel_backward=True, handover=True) if handover else plan.capture(x, w, y)
     for t in outs():
         t.zero_()
     for _ in range(3):                      # replays reuse the workspace (tickets, exchange epochs) left by the previous one
@@ -338,6 +343,44 @@ def test_head_headline_shape_vs_oracle(precision, dx_dtype):
     np.testing.assert_allclose(plan.p_target.cpu().numpy(), ref["p_target"], rtol=2e-3, atol=1e-7)
     np.testing.assert_allclose(plan.p_max.cpu().numpy(), ref["p_max"], rtol=2e-3, atol=1e-7)
     assert plan.label_counts.tolist() == [int((y >= 0).sum()), int((y < 0).sum()), 0, 0]
+
+
+def test_head_headline_shape_graph_handover_is_bit_identical():
+    """The headline shape as one CUDA graph with the row-tile hand-over (forward -> {dW GEMM fed by the row-tile flags ||
+    dX || label statistics}; opt-in, see HeadPlan.capture for why it is not the default) against the plain eager step of
+    the same plan: dW, dX, loss bit for bit, over several replays."""
+    plan, _, (xt, wt, yt) = _plan_case(16384, 2048, 1000, "entropic", 6, "fast", torch.bfloat16)
+    plan.step(xt, wt, yt)
+    torch.cuda.synchronize()
+    ref = [t.clone() for t in (plan.loss, plan.dw, plan.dx)]
+    graph = plan.capture(xt, wt, yt, parallel_backward=True, handover=True)
+    for rep in range(4):
+        for t in (plan.loss, plan.dw, plan.dx):
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for got, want in zip((plan.loss, plan.dw, plan.dx), ref):
+            assert torch.equal(got, want), rep
+
+
+def test_head_backward_handover_flag_without_a_publishing_forward_falls_back():
+    """OSB_BWD_DZ_FROM_PREV_FORWARD is a promise about the kernel in front.  A caller that breaks it (here: the forward ran
+    WITHOUT OSB_FWD_PUBLISH_ROW_TILES, so no row-tile word is ever set) must get the plain dependency back after the
+    time-out, not a hang and not a wrong gradient."""
+    import time
+    from openset_imagenet_b200 import _lib as L
+    plan, _, (xt, wt, yt) = _plan_case(1500, 256, 300, "entropic", 7, "exact", torch.float32)
+    plan.step(xt, wt, yt)
+    torch.cuda.synchronize()
+    ref = plan.dw.clone()
+    plan.dw.zero_()
+    plan.label_stats(yt)
+    plan.forward(xt, wt, yt)
+    t0 = time.perf_counter()
+    plan.backward_dw(xt, wt, flags=L.BWD_DZ_FROM_PREV_FORWARD)
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 5.0
+    assert torch.equal(plan.dw, ref)
 
 
 def test_head_bg_protocol_shape_vs_oracle():

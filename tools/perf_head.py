@@ -48,9 +48,9 @@ def head_case(B, K, C, variant="entropic"):
                       num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), dz.data_ptr(), lddz, PLANES, 0, 0, ws.data_ptr(), ws.numel(), st)
     def fwd_nodz(): L.call("osb_head_forward", x.data_ptr(), K, w.data_ptr(), None, y.data_ptr(), L.ptr(cw), B, K, C, vnum, 1.0, -100, den.data_ptr(), C,
                       num.data_ptr(), loss.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), pred.data_ptr(), None, lddz, PLANES, 0, 0, ws.data_ptr(), ws.numel(), st)
-    def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, PLANES, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, L.BF16, None, None, 0, ws.data_ptr(), ws.numel(), st)
-    def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, PLANES, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, None, K, L.BF16, dw.data_ptr(), None, 0, ws.data_ptr(), ws.numel(), st)
-    def bdwp(): L.call("osb_head_backward_dw_partials", dz.data_ptr(), lddz, PLANES, x.data_ptr(), K, B, K, C, None, ws.data_ptr(), ws.numel(), st)
+    def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, PLANES, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, L.BF16, None, None, 0, 0, ws.data_ptr(), ws.numel(), st)
+    def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, PLANES, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, None, K, L.BF16, dw.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), st)
+    def bdwp(): L.call("osb_head_backward_dw_partials", dz.data_ptr(), lddz, PLANES, x.data_ptr(), K, B, K, C, None, 0, 0, ws.data_ptr(), ws.numel(), st)
     def step(): lab(); fwd(); bdx(); bdw()
     fl = 2.0 * B * K * C
     print(f"--- head B={B} K={K} C={C} {variant}: GEMM flops each {fl/1e9:.2f} GF")

@@ -14,7 +14,7 @@ den = torch.ones(1, dtype=torch.float64, device=dev)
 st = L.stream_ptr(dev)
 lib = L.load()
 lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
-def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, 1, den.data_ptr(), x.data_ptr(), K, x.data_ptr(), B, K, C, None, None, K, L.BF16, dw.data_ptr(), None, 0, ws.data_ptr(), ws.numel(), st)
+def bdw(): L.call("osb_head_backward", dz.data_ptr(), lddz, 1, den.data_ptr(), x.data_ptr(), K, x.data_ptr(), B, K, C, None, None, K, L.BF16, dw.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), st)
 for _ in range(3): bdw()
 torch.cuda.synchronize()
 trace = torch.zeros(512, 64, dtype=torch.int64, device=dev)

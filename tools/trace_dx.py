@@ -15,7 +15,7 @@ den = torch.ones(1, dtype=torch.float64, device=dev)
 st = L.stream_ptr(dev)
 lib = L.load()
 lib.osb_debug_set_head_trace.argtypes = [ctypes.c_void_p]
-def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, 1, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, L.BF16, None, None, int(os.environ.get("OSB_CTAS", "0")), ws.data_ptr(), ws.numel(), st)
+def bdx(): L.call("osb_head_backward", dz.data_ptr(), lddz, 1, den.data_ptr(), x.data_ptr(), K, w.data_ptr(), B, K, C, None, dx.data_ptr(), K, L.BF16, None, None, int(os.environ.get("OSB_CTAS", "0")), 0, ws.data_ptr(), ws.numel(), st)
 lib.osb_debug_set_head_dbg(int(os.environ.get('OSB_DBG', '0')))
 for _ in range(3): bdx()
 torch.cuda.synchronize()
