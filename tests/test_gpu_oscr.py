@@ -239,6 +239,44 @@ def test_oscr_full_size_properties():
     np.testing.assert_array_equal(fc, o_fc)
 
 
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (37.5, -11.0), (1e-30, 0.0), (0.0, 0.75)])
+def test_oscr_radix_passes_cover_the_whole_key(scale, shift):
+    """The radix passes must cover all 32 bits of the order-preserving key: scores as probabilities, raw logits of both
+    signs and large magnitude, denormal-sized values and a constant matrix (every key equal) all give the oracle's curve
+    bit for bit."""
+    from openset_imagenet_b200.util import calculate_oscr_device
+    rng = np.random.default_rng(11)
+    N, C = 60000, 24
+    s = (rng.standard_normal((N, C)) * scale + shift).astype(np.float32)
+    gt = O.make_labels(N, C, 0.4, seed=12)
+    gt[::9] = np.where(gt[::9] < 0, -2, gt[::9])
+    o_taus, o_cc, o_fc, n_kn, n_unk = O.oscr_counts(gt, s, -1)
+    r = calculate_oscr_device(gt, s, -1)
+    n = max(int(r.meta[0]) - 1, 0)
+    assert n == len(o_taus) and int(r.meta[1]) == n_kn and int(r.meta[3]) == n_unk
+    np.testing.assert_array_equal(r.taus[:n].cpu().numpy(), o_taus)
+    np.testing.assert_array_equal(r.ccr_cnt[:n].cpu().numpy(), o_cc)
+    np.testing.assert_array_equal(r.fpr_cnt[:n].cpu().numpy(), o_fc)
+
+
+def test_oscr_more_records_than_one_tile_per_cta():
+    """More records than 148 CTAs x 8192 hold at once: every CTA sorts several tiles per pass (the records no longer stay
+    in registers between the count and the scatter phase).  1.6 M rows x 4 columns, all of them known or unk."""
+    from openset_imagenet_b200.util import calculate_oscr_device
+    rng = np.random.default_rng(5)
+    N, C = 1_600_000, 4
+    s = rng.random((N, C), dtype=np.float32)
+    s[::3] = np.round(s[::3], 3)                                        # plenty of ties as well
+    gt = rng.integers(-1, C, size=N).astype(np.int64)
+    o_taus, o_cc, o_fc, n_kn, n_unk = O.oscr_counts(gt, s, -1)
+    r = calculate_oscr_device(gt, s, -1)
+    n = max(int(r.meta[0]) - 1, 0)
+    assert n == len(o_taus) and int(r.meta[1]) == n_kn and int(r.meta[3]) == n_unk and n_kn + n_unk == N
+    np.testing.assert_array_equal(r.taus[:n].cpu().numpy(), o_taus)
+    np.testing.assert_array_equal(r.ccr_cnt[:n].cpu().numpy(), o_cc)
+    np.testing.assert_array_equal(r.fpr_cnt[:n].cpu().numpy(), o_fc)
+
+
 @pytest.mark.parametrize("name", ["synth_m1", "synth_m2"])
 def test_ccr_at_fpr_golden(golden, name):
     import openset_imagenet_b200 as osb
