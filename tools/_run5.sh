@@ -1,0 +1,13 @@
+cd $GRAFT_REPO_ROOT
+N=${1:-2}
+timeout -s USR1 -k 20 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r03_bench_n${N}_full.json 2> gpurun_out/r03_bench_n${N}_full.err; echo "bench rc=$?"
+tail -5 gpurun_out/r03_bench_n${N}_full.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r03_bench_n${N}_full.json").read().strip().splitlines()[-1])
+print("step us", d["ms_per_step"]*1e3, "value", d["value"], "e2e", d["e2e"] and (d["e2e"]["value"], d["e2e"]["ms_per_step"]))
+print("parity", json.dumps(d["parity"])[:900])
+o=d.get("oscr"); print("oscr", o and (o["value"], o["config"]["launch"], o.get("parity")))
+b=d.get("bg"); print("bg", b and (b["us_per_step"], b["value"], b["parity"].get("sharded")))
+print("roofline", json.dumps(d["roofline"])[:700])
+PY
