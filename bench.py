@@ -341,7 +341,8 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     bracket_sum = sum(kernels.values())
     roof.update({
         "kernel": dom, "achieved": gemm_flops / kernels[dom] / 1e6, "peak": peak_k, "peak_kind": peak_kind_k,
-        "traffic": (load_traffic().get(dom, {}).get("bytes") if (B, K, C) == (16384, 2048, 1000) else None),
+        "traffic": ((load_traffic().get(dom) or load_traffic().get(dom.split(" ")[0], {})).get("bytes")
+                    if (B, K, C) == (16384, 2048, 1000) else None),
         "traffic_note": "dram read+write bytes of one launch from the committed ncu --set full capture (profiles/traffic.json)",
         "kernels_us": {k: round(v, 2) for k, v in kernels.items()},
         "kernels_tflops": {k: round(gemm_flops / v / 1e6, 1) for k, v in kernels.items()},

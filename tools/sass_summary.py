@@ -10,7 +10,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "openset_imagenet
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 GROUPS = collections.OrderedDict([
     ("UTCHMMA (tcgen05.mma, bf16)", r"\bUTCHMMA"), ("UTCBAR (tcgen05.commit)", r"\bUTCBAR"), ("LDTM (tcgen05.ld)", r"\bLDTM"),
-    ("STTM (tcgen05.st)", r"\bSTTM"), ("UTMALDG (TMA tensor load)", r"\bUTMALDG"), ("UTMASTG (TMA tensor store)", r"\bUTMASTG"),
+    ("STTM (tcgen05.st)", r"\bSTTM"), ("UTMALDG (TMA tensor load)", r"\bUTMALDG"), ("UTMASTG (TMA tensor store)", r"\bUTMASTG"), ("UTMAREDG (TMA tensor reduce-add)", r"\bUTMAREDG"),
     ("UTMAPF (TMA L2 prefetch)", r"\bUTMAPF"), ("UBLKCP (cp.async.bulk)", r"\bUBLKCP"), ("SYNCS (mbarrier)", r"\bSYNCS"),
     ("UCGABAR (cluster barrier)", r"\bUCGABAR"), ("multimem (LDGMC / STG.MC / REDG.MC)", r"MULTIMEM|LDGMC|\.MC\b|\bSTGMC|\bREDGMC"),
     ("HMMA (mma.sync)", r"\bHMMA"), ("ACQBULK / fence.proxy", r"\bACQBULK|FENCE\.VIEW\.ASYNC"),
