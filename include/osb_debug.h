@@ -14,6 +14,7 @@ void osb_debug_set_head_splitk(int on);            /* 0: small batches take the 
 int  osb_debug_head_splitk_max_clusters(void);     /* clusters of 8 CTAs resident at once (split-K forward) */
 void osb_debug_set_head_dbg(int bits);             /* dX probes: 1 stale operands, 2 no TMEM drain, 8 no stores */
 void osb_debug_set_head_trace(void* device_buf);   /* [grid][64] int64 phase stamps of the head kernels, or NULL */
+void osb_debug_set_dw_trace(void* device_buf);     /* [grid][8] int64 stamps of the dW GEMM alone (tools/timeline.py), or NULL */
 void osb_debug_set_allreduce_timeout(long long cycles);   /* give-up time of the peer kernels, 0 = default (~2 s) */
 void osb_debug_set_exchange_timeout(long long cycles);    /* same for osb_oscr_exchange */
 void osb_debug_set_curve_trace(void* device_buf);  /* [grid][32] int64 SM clock stamps of oscr_curve_kernel, or NULL */

@@ -715,10 +715,18 @@ template <bool F32OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDx2Threads, 1)
 head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_dx, int B, int K, int C, int planes,
-                const float* __restrict__ gscale, const double* __restrict__ den, long long* trace, int dbg) {
+                const float* __restrict__ gscale, const double* __restrict__ den,
+                float4* __restrict__ zero_dst, unsigned long long zero_n4, long long* trace, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint8_t* sStage = smem + kDx2OffStage;
+    if (zero_dst) {
+        // dW for the GEMM behind this kernel, whose batch splits both ADD their tile at the destination: every CTA clears a
+        // slice on its way in (nothing in front of this launch touches dW, so this runs under the forward's tail)
+        const unsigned long long per = (zero_n4 + gridDim.x - 1) / gridDim.x;
+        const unsigned long long lo = per * blockIdx.x, hi = lo + per < zero_n4 ? lo + per : zero_n4;
+        for (unsigned long long i = lo + threadIdx.x; i < hi; i += kDx2Threads) zero_dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDx2OffBars);
     uint64_t* full = bars; uint64_t* empty = full + kDx2Stages;
     uint64_t* t_full = empty + kDx2Stages; uint64_t* t_empty = t_full + 2;
@@ -1148,6 +1156,14 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
 #pragma unroll
                 for (int g = 0; g < kDwBN / 32; ++g)
                     tma_store_3d(&tm_part, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, row0, sp);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+            } else if (direct == 2) {
+                // dW was cleared by the kernel in front: both splits add at the destination, nobody waits for anybody
+                // (0 + a + b is the same bits in either order)
+#pragma unroll
+                for (int g = 0; g < kDwBN / 32; ++g)
+                    tma_reduce_add_2d(&tm_dw, my_stage + g * kStageWarpBytes, nt * kDwBN + g * 32, row0);
                 tma_store_commit();
                 tma_store_wait_read<0>();
             } else {
@@ -1675,6 +1691,10 @@ static int g_dbg = 0;
 extern "C" void osb_debug_set_head_dbg(int v) { g_dbg = v; }
 // developer hook (osb_debug.h): device buffer of [grid][64] int64 clock stamps, or NULL
 extern "C" void osb_debug_set_head_trace(void* p) { g_trace = reinterpret_cast<long long*>(p); }
+// developer hook (osb_debug.h): a separate stamp buffer for the dW GEMM ([grid][8]: entry, mainloop done, epilogue done, exit), so that one
+// replay of a whole step can be laid out on a time line (tools/timeline.py); NULL = the dW GEMM stamps into the head trace
+static long long* g_trace_dw = nullptr;
+extern "C" void osb_debug_set_dw_trace(void* p) { g_trace_dw = reinterpret_cast<long long*>(p); }
 
 // launch configuration with programmatic stream serialization: the kernel's prologue may overlap the tail of the kernel in
 // front of it on the stream; the kernel itself calls pdl_wait before it touches anything that kernel produces
@@ -1793,7 +1813,8 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
 // *direct_out says whether that happened
 static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, int64_t ldx, int64_t B, int K, int C,
                        void* ws, cudaStream_t st, int* splits_out, bool row_flags, float* direct_dw = nullptr,
-                       const float* gscale = nullptr, const double* den = nullptr, bool* direct_out = nullptr) {
+                       const float* gscale = nullptr, const double* den = nullptr, bool* direct_out = nullptr,
+                       bool prezeroed = false) {
     CUtensorMap tdz, tx;
     OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, 64), "dz (MN-major)");
     OSB_TMAP(make_tmap_bf16(&tx, x, (uint64_t)B, (uint64_t)K, (uint64_t)ldx, 64), "x (MN-major)");
@@ -1819,8 +1840,9 @@ static int run_dw_gemm(const void* dz, int64_t lddz, int planes, const void* x, 
         // the forward's units: ceil(C / 256) class slices x 2 CTAs publish one word per epilogue warp and row tile
         const unsigned int* rflags = (row_flags && row_flags_usable(B, K, C))
                                          ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(ws) + kWsOffRowFlags) : nullptr;
-        OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, tdw, (int)B, K, C, planes, splits, direct ? 1 : 0, gscale, den,
-                                    flags, rflags, ((C + 255) / 256) * 2, g_trace));
+        OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dw2_kernel, tdz, tx, tpart, tdw, (int)B, K, C, planes, splits,
+                                    direct ? ((prezeroed && splits == 2) ? 2 : 1) : 0, gscale, den,
+                                    flags, rflags, ((C + 255) / 256) * 2, g_trace_dw ? g_trace_dw : g_trace));
     } else {
         rc = set_smem(head_dw_kernel, kDwSmemBytes);
         if (rc) return rc;
@@ -1859,6 +1881,12 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
     OSB_REQUIRE(((uintptr_t)w % 16 == 0) && ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dw % 16 == 0) && max_ctas >= 0, OSB_ERR_ARG,
                 "osb_head_backward: w, dx and dw must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    // dX and dW in one call, and a dW GEMM of two batch splits that writes dW itself: the dX kernel clears dW on its way in
+    // and both splits add their tile at the destination without waiting for each other
+    static const bool no_prezero = getenv("OSB_NO_DW_PREZERO") != nullptr;           // developer A/B switch
+    const bool prezero = dx && dw && !no_prezero && osb_head_dw_is_direct(B, K, C) && dw_splits((int)B, K, C) == 2;
+    float4* zero_dst = prezero ? reinterpret_cast<float4*>(dw) : nullptr;
+    const unsigned long long zero_n4 = prezero ? (unsigned long long)C * (unsigned long long)K / 4ull : 0ull;
     if (dx) {
         CUtensorMap tdz, tw, tdx;
         OSB_TMAP(make_tmap_bf16_3d(&tdz, dz, (uint64_t)dz_planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, BM), "dz (K-major)");
@@ -1873,12 +1901,12 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
             OSB_TMAP(make_tmap_f32_2d(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx (fp32)");
             rc = set_smem(head_dx2_kernel<true>, kDx2SmemBytes);
             if (rc) return rc;
-            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel<true>, tdz, tw, tdx, (int)B, K, C, dz_planes, gscale, den, g_trace, g_dbg));
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel<true>, tdz, tw, tdx, (int)B, K, C, dz_planes, gscale, den, zero_dst, zero_n4, g_trace, g_dbg));
         } else {
             OSB_TMAP(make_tmap_bf16(&tdx, dx, (uint64_t)B, (uint64_t)K, (uint64_t)lddx, 32), "dx");
             rc = set_smem(head_dx2_kernel<false>, kDx2SmemBytes);
             if (rc) return rc;
-            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel<false>, tdz, tw, tdx, (int)B, K, C, dz_planes, gscale, den, g_trace, g_dbg));
+            OSB_CUDA(cudaLaunchKernelEx(&cfg, head_dx2_kernel<false>, tdz, tw, tdx, (int)B, K, C, dz_planes, gscale, den, zero_dst, zero_n4, g_trace, g_dbg));
         }
     }
     if (dw) {
@@ -1886,7 +1914,7 @@ extern "C" int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, co
         bool direct = false;
         // the dW GEMM is directly behind the forward only when this call launches no dX in front of it
         rc = run_dw_gemm(dz, lddz, dz_planes, x, ldx, B, K, C, ws, st, &splits, (flags & OSB_BWD_DZ_FROM_PREV_FORWARD) && !dx,
-                         dw, gscale, den, &direct);
+                         dw, gscale, den, &direct, prezero);
         if (rc) return rc;
       if (!direct) {
         const float* partials = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + kWsOffDw);

@@ -134,6 +134,13 @@ class HeadPlan:
                L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), L.ptr(self.dx), self.K, self._dx_code(),
                None, None, int(max_ctas), 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
+    def backward(self, x, w, gscale=None, den=None, max_ctas=0):
+        """dX, then dW (+ db), from ONE call: with two batch splits the dX kernel clears dW on its way in and both splits of
+        the dW GEMM add their tile at the destination without waiting for each other (``osb_head_backward`` with dx and dw)."""
+        L.call("osb_head_backward", L.ptr(self.dz), self.lddz, self.planes, L.ptr(self.den_step if den is None else den),
+               L.ptr(x), self.K, L.ptr(w), self.B, self.K, self.C, L.ptr(gscale), L.ptr(self.dx), self.K, self._dx_code(),
+               L.ptr(self.dw), L.ptr(self.db), int(max_ctas), 0, L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+
     def backward_dw(self, x, w, gscale=None, den=None, flags=0):
         """``flags=L.BWD_DZ_FROM_PREV_FORWARD``: this launch is directly behind ``forward(..., flags=L.FWD_PUBLISH_ROW_TILES)``
         on the stream; the dW GEMM then starts on the SMs the forward leaves idle and takes dZ row tile by row tile."""
@@ -196,10 +203,9 @@ class HeadPlan:
                 self.backward_dw(x, w, gscale, flags=take)
                 side.wait_stream(branch)
             else:
-                self.backward_dx(x, w, gscale)
                 if side_labels:
                     labels_beside()
-                self.backward_dw(x, w, gscale)
+                self.backward(x, w, gscale)
             if side_labels:
                 side.wait_stream(lbranch)
 
@@ -224,8 +230,7 @@ class HeadPlan:
         self.label_stats(y, den_scale_hook)
         den = self.den if den_scale_hook is not None else None
         self.forward(x, w, y, bias, want_pred=want_pred, den="step" if den is None else den)
-        self.backward_dx(x, w, gscale, den=den)
-        self.backward_dw(x, w, gscale, den=den)
+        self.backward(x, w, gscale, den=den)
 
 
 class OscrPlan:
