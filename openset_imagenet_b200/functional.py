@@ -166,8 +166,9 @@ class HeadPlan:
         # dZ, so they become parallel branches of the graph.  Large batches fill the GPU with either kernel and stay serial:
         # under a full load the chip is power-limited (the SM clock falls from 1.85 to 1.58 GHz between 16 and 148 busy
         # SMs within one launch), so kernels that overlap only share the same budget -- measured at 16384 x 2048 -> 1000,
-        # 12 + 6 interleaved runs on one box: serial 184.9 us, parallel branches 184.8 us, parallel branches with the
-        # row-tile hand-over (``handover=True``: the dW GEMM starts under the forward on the SMs it leaves idle) 194.8 us.
+        # interleaved runs on one box: serial 182.9 us, parallel branches with the dW GEMM launched first 182.0 us, the same
+        # with the row-tile hand-over (``handover=True``: the first dW CTA pairs run under the forward on the SMs it leaves
+        # idle and are done 25 us before the others) 187.1 us; time lines in profiles/r02_probe_power_and_fill.txt.
         fork = self.B <= 4096 if parallel_backward is None else bool(parallel_backward)
         pub = L.FWD_PUBLISH_ROW_TILES if (fork and handover) else 0
         take = L.BWD_DZ_FROM_PREV_FORWARD if (fork and handover) else 0
@@ -198,9 +199,16 @@ class HeadPlan:
                 # dX on the branch; the longer chain (dW GEMM + split-K reduce) stays on the stream of the forward kernel,
                 # where each kernel is launched programmatically behind the one in front of it
                 branch.wait_stream(side)
-                with torch.cuda.stream(branch):
-                    self.backward_dx(x, w, gscale)
-                self.backward_dw(x, w, gscale, flags=take)
+                if handover:
+                    # both kernels are programmatic dependents of the forward and the one launched first takes the SMs
+                    # first: the dW GEMM, which consumes dZ as it is published
+                    self.backward_dw(x, w, gscale, flags=take)
+                    with torch.cuda.stream(branch):
+                        self.backward_dx(x, w, gscale)
+                else:
+                    with torch.cuda.stream(branch):
+                        self.backward_dx(x, w, gscale)
+                    self.backward_dw(x, w, gscale)
                 side.wait_stream(branch)
             else:
                 if side_labels:
