@@ -252,9 +252,12 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
     # epoch lives in device memory).  Only the NCCL fallback stays eager.
     launch_mode = "eager"
     run_step = eager_step
+    n_launch = sp.launches_per_step
     if not args.eager and (world == 1 or sp.peer is not None):
         graphs = [(plan.capture(xs[i], w, ys[i]) if world == 1 else sp.capture(xs[i], w, ys[i])) for i in range(nbuf)]
-        launch_mode = "CUDA-graph replay of the whole step" + (" incl. the peer-memory all-reduce" if world > 1 else f" ({plan.launches_per_step} kernels)")
+        n_launch = plan.launches_per_captured_step if world == 1 else sp.launches_per_step
+        launch_mode = "CUDA-graph replay of the whole step" + (" incl. the peer-memory all-reduce" if world > 1 else
+                                                                f" ({n_launch} kernels" + ("; forward and dX are one kernel)" if plan.fused_dx and n_launch < plan.launches_per_step else ")"))
 
         def run_step(i):
             graphs[i % nbuf].replay()
@@ -309,7 +312,7 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
         parity["sharded"] = sharded_parity(cfg, sp, xs[0], w, ys[0], plan_kw, rank, world, dev)
     if light:
         return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=None, clocks=clocks, loss=loss_val,
-                    launches=sp.launches_per_step * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
+                    launches=n_launch * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
                     precision=parity.get("head", {}).get("precision"))
 
     # ---- per-kernel times: a second, shorter loop with CUDA events between the launches of an EAGER step, queued behind
@@ -416,7 +419,7 @@ def run_head(args, cfg, rank, world, dev, peaks, light=False):
                        "loss read back every step; dX and dW stay on the device for the backbone / optimiser",
                "host_thread_cpus": len(os.sched_getaffinity(0))}
     return dict(value=value, ms_per_step=ms_per_step, roofline=roof, e2e=e2e, clocks=clocks, loss=loss_val,
-                launches=sp.launches_per_step * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
+                launches=n_launch * args.steps, allreduce=allreduce, launch_mode=launch_mode, parity=parity,
                 precision=parity.get("head", {}).get("precision"))
 
 

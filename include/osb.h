@@ -158,6 +158,21 @@ int osb_head_backward(const void* dz, int64_t lddz, int dz_planes, const double*
                       const void* w, int64_t B, int K, int C, const float* gscale,
                       void* dx, int64_t lddx, int dx_dtype, float* dw, float* db, int max_ctas, int flags,
                       void* ws, size_t ws_bytes, void* stream);
+/* Forward and dX of a training step from ONE call: loss / row outputs / dz as osb_head_forward (no per-row predictions),
+ * dx = gscale[0] / den[0] * dz @ w as osb_head_backward.  Where osb_head_forward_dx_is_fused(B, K, C) says 1 (heads wider
+ * than 128 classes on the persistent forward) it is ONE kernel: the grid covers every SM, the CTA pairs the forward
+ * leaves idle start with dX tiles at once (taking the rows of dz as the forward publishes them, 256-row tile by tile),
+ * and every other pair goes on with dX tiles on the same pipeline state the moment its last forward MMA is issued, so
+ * its first dX tiles run under the forward's last epilogue.  Elsewhere the two kernels run one after the other.  The
+ * same bits either way.  den must not be NULL (it scales dx). */
+int osb_head_forward_dx(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
+                        const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
+                        int64_t ignore_index, const double* den, int valid_cols,
+                        double* loss_num, float* loss, float* row_ptgt, float* row_pmax,
+                        void* dz, int64_t lddz, int dz_planes, const float* gscale,
+                        void* dx, int64_t lddx, int dx_dtype, int flags, int max_ctas,
+                        void* ws, size_t ws_bytes, void* stream);
+int osb_head_forward_dx_is_fused(int64_t B, int K, int C);
 /* 1 when osb_head_forward runs this shape as the split-K cluster kernel (small batches, C <= 256), else 0 */
 int osb_head_forward_is_splitk(int64_t B, int K, int C);
 /* 1 when osb_head_backward writes dW straight from the GEMM (at most two batch splits: the first stores, the second adds

@@ -39,6 +39,9 @@ SIGNATURES = {
     "osb_head_forward": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _i64, _p, _i,
                               _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
     "osb_head_backward": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _i64, _i, _i, _p, _p, _i64, _i, _p, _p, _i, _i, _p, _sz, _p]),
+    "osb_head_forward_dx": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _i64, _p, _i,
+                                 _p, _p, _p, _p, _p, _i64, _i, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
+    "osb_head_forward_dx_is_fused": (_i, [_i64, _i, _i]),
     "osb_head_forward_is_splitk": (_i, [_i64, _i, _i]),
     "osb_head_dw_is_direct": (_i, [_i64, _i, _i]),
     "osb_head_dw_partials_offset": (_sz, []),

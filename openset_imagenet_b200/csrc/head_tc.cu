@@ -19,6 +19,7 @@
 // Reference arithmetic: model.py:23-26,37-38 (linear), losses.py:16-29 / train.py:343,347 (losses),
 // train.py:177 + metrics.py:33-40 + util.py:109-111 (the per-row statistics), autograd of those.
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 #include "osb_common.cuh"
 #include "row_modes.cuh"
@@ -42,6 +43,7 @@ constexpr int kMaxXid = 80;             // row blocks that exchange statistics a
 constexpr size_t kXchStatBytes = (size_t)kMaxXid * 2 * 4 * 128 * 6 * sizeof(uint2);
 // workspace (zeroed once by the caller): [ticket, exchange epoch][loss partials][exchange statistics][dW partials]
 constexpr size_t kWsOffEpoch = 64;
+constexpr size_t kWsOffFlagEpoch = 72;
 constexpr size_t kWsOffPartials = kHeadTicketBytes;
 constexpr size_t kWsOffStats = kWsOffPartials + sizeof(double) * kMaxPartials;
 // [dW tile flags]: one word per (output tile, CTA of the pair, epilogue warp): "split 0 has stored these rows" (direct dW)
@@ -133,6 +135,221 @@ __device__ __forceinline__ void stage_chunk(uint8_t* sbuf, int row, int chunk, c
     *reinterpret_cast<uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
 }
 
+constexpr int kDxBN = 256;
+// =================================================================================================
+// dX = g * dZ W with CTA pairs (cta_group::2): A = dZ tile (K-major over classes), B = W tile viewed MN-major (N = feature
+// index); one cluster of 2 CTAs per 256 rows x 256 features, M = 256 MMAs.  The K loop runs over the classes of every dZ
+// plane (plane 1 = rounding residual of plane 0, the W k-block is the same).
+// CTA r of the pair loads rows [128 r, +128) of the dZ tile and features [128 r, +128) of the W tile (32 KB per stage
+// instead of 48 KB), the leader issues the MMAs, each CTA drains its own 128 x 256 accumulator from its TMEM.
+// =================================================================================================
+// kDx2EW warps per TMEM lane quadrant drain the accumulator.
+constexpr int kDx2EW = 2;
+constexpr int kDx2Threads = (2 + 4 * kDx2EW) * 32;
+constexpr int kDx2Stages = 5;
+constexpr int kDx2StageBytes = kABytes + 2 * kBoxBytes;         // 32 KB per CTA
+constexpr int kDx2OffStage = kDx2Stages * kDx2StageBytes;
+constexpr int kDx2OffBars = kDx2OffStage + 4 * (kDxBN / 64) * kStageWarpBytes;      // one staging buffer per (quadrant, 64-column box)
+constexpr int kDx2SmemBytes = kDx2OffBars + (2 * kDx2Stages + 4) * 8 + 16 + 1024;
+static_assert(kDx2SmemBytes <= 232448, "dx2 kernel shared memory");
+
+// ---- the three roles of the dX GEMM as device functions: head_dx2_kernel runs them on their own, the fused forward + dX
+// kernel runs them behind its forward loops on the SAME pipeline state (stage ring, TMEM buffers, barriers), so that a
+// CTA pair's first dX tiles run under the forward's last epilogue ----
+struct DxShape {
+    int B, K, C, planes;
+    int first, stride;                  // tiles first, first + stride, ... (row-tile major: tile = mt * n_tiles + nt)
+};
+
+// Wait until the forward has published the 256-row tile `rt` of dZ (row-tile words of the workspace, see
+// OSB_FWD_PUBLISH_ROW_TILES): lanes 8j .. 8j+7 look at the (up to) 8 slots x 8 warp words of row tile rt + j, four tiles per
+// poll.  `target`: the value a published word holds.  Returns false when nothing arrived for 0.5 s.
+__device__ __forceinline__ bool wait_row_tiles(const unsigned int* row_flags, unsigned int target, int rt, int n_row_tiles, int slots,
+                                               int lane, int& ready_lo, int& ready_hi) {
+    if (rt >= ready_lo && rt < ready_hi) return true;
+    const int j = rt + (lane >> 3), slot = lane & 7;
+    const bool mine = j < n_row_tiles && slot < slots;
+    const unsigned int* fp = row_flags + ((size_t)j * 8 + slot) * 8;
+    const long long t0 = gtime();
+    unsigned got;
+    bool alive = true;
+    for (;;) {
+        bool ok = true;
+        if (mine) {
+            uint32_t f[8];
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]) : "l"(fp) : "memory");
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]) : "l"(fp + 4) : "memory");
+            ok = f[0] == target && f[1] == target && f[2] == target && f[3] == target &&
+                 f[4] == target && f[5] == target && f[6] == target && f[7] == target;
+        }
+        got = __ballot_sync(0xffffffffu, ok);
+        if ((got & 0xffu) == 0xffu) break;
+        if (__any_sync(0xffffffffu, gtime() - t0 > 500000000LL)) { alive = false; break; }
+        __nanosleep(256);
+    }
+    __threadfence();                                    // acquire side of the words' release
+    asm volatile("fence.proxy.async;" ::: "memory");    // the loads that follow are TMA (async proxy) reads
+    if (!alive) return false;
+    int n = 1;
+    while (n < 4 && ((got >> (8 * n)) & 0xffu) == 0xffu) ++n;
+    ready_lo = rt; ready_hi = rt + n;
+    return true;
+}
+
+template <int STAGES>
+__device__ __forceinline__ void dx_producer(uint8_t* smem, uint64_t* full, uint64_t* empty, uint32_t& it, const CUtensorMap* tm_dz,
+                                            const CUtensorMap* tm_w, const DxShape& d, int rank, int lane, int dbg,
+                                            const unsigned int* row_flags, unsigned int flag_target, int flag_slots) {
+    const int n_tiles = (d.K + kDxBN - 1) / kDxBN, total = ((d.B + 255) / 256) * n_tiles;
+    const int n_kb1 = (d.C + BK - 1) / BK, n_kb = n_kb1 * d.planes;
+    int ready_lo = 0, ready_hi = 0;
+    for (int tile = d.first; tile < total; tile += d.stride) {
+        const int mt = tile / n_tiles, nt = tile % n_tiles;
+        if (row_flags && !wait_row_tiles(row_flags, flag_target, mt, (d.B + 255) / 256, flag_slots, lane, ready_lo, ready_hi)) {
+            ready_lo = 0; ready_hi = 1 << 30;           // the forward never published (it cannot happen inside one kernel): go on
+        }
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+            const int pl = kb >= n_kb1 ? 1 : 0, kc = kb - pl * n_kb1;
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * kDx2StageBytes;
+            if (elect_one()) {
+                if ((dbg & 1) && it >= STAGES) {        // developer probe: MMA rate without operand traffic (stale tiles)
+                    if (rank == 0) mbar_arrive(&full[s]);
+                } else {
+                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDx2StageBytes);     // both CTAs' bytes land on the leader's barrier
+                    tma_load_3d_2sm(st, tm_dz, &full[s], kc * BK, mt * 256 + rank * 128, pl);            // 64 classes x 128 rows
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)                                                         // 64 features x 64 classes
+                        tma_load_2d_2sm(st + kABytes + j * kBoxBytes, tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kc * BK);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int STAGES>
+__device__ __forceinline__ void dx_mma(uint8_t* smem, uint64_t* full, uint64_t* empty, uint64_t* t_full, uint64_t* t_empty,
+                                       uint32_t& it, uint32_t& tc, uint32_t tbase, const DxShape& d, int lane, long long* trace) {
+    const int n_tiles = (d.K + kDxBN - 1) / kDxBN, total = ((d.B + 255) / 256) * n_tiles;
+    const int n_kb1 = (d.C + BK - 1) / BK, n_kb = n_kb1 * d.planes;
+    const uint32_t idesc = make_idesc_bf16(256, kDxBN, false, true);
+    uint32_t tn = 0;
+    for (int tile = d.first; tile < total; tile += d.stride, ++tc, ++tn) {
+        const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+        mbar_wait(&t_empty[buf], tph ^ 1);
+        tc_fence_after_sync();
+        if (trace && tn < 8 && lane == 0) { trace[blockIdx.x * 64 + tn * 8 + 0] = gtime(); trace[blockIdx.x * 64 + tn * 8 + 7] = clock64(); }
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after_sync();
+            if (trace && blockIdx.x == 0 && tn >= 1 && tn < 3 && lane == 0) trace[256 * 64 + (tn - 1) * 32 + kb] = clock64();
+            const uint32_t a_addr = smem_u32(smem + s * kDx2StageBytes);
+            const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_mnmajor(a_addr + kABytes, kBoxBytes);
+            const int rem = d.C - (kb >= n_kb1 ? kb - n_kb1 : kb) * BK;
+            const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    if (k < ksteps) umma2_bf16(tbase + buf * kDxBN, adesc + 2 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
+                umma2_commit_mc(&empty[s]);
+                if (kb == n_kb - 1) umma2_commit_mc(&t_full[buf]);
+            }
+            __syncwarp();
+        }
+        if (trace && tn < 8 && lane == 0) trace[blockIdx.x * 64 + tn * 8 + 2] = gtime();
+    }
+}
+
+// warp (q, hh): lane quadrant q, column half hh.  A thread pulls its 128 accumulator columns into registers with one
+// TMEM sweep and hands the buffer back to the MMA warp at once; conversion, staging and the TMA stores run after
+// that.  Every 64-column box has its own staging buffer, so nothing waits for a store issued in the same tile
+// (with two buffers per warp and four boxes per tile the drain waited ~0.5 us per box for the store two boxes
+// back to finish reading, 4.5 us per tile against 5.3 us of MMAs).
+template <bool F32OUT>
+__device__ __forceinline__ void dx_epilogue(uint8_t* sStage, uint64_t* t_full, uint64_t* t_empty, uint32_t& tc, uint32_t tbase,
+                                            const CUtensorMap* tm_dx, const DxShape& d, int rank, int warp, int lane,
+                                            const float* gscale, const double* den, long long* trace, int dbg) {
+    const int n_tiles = (d.K + kDxBN - 1) / kDxBN, total = ((d.B + 255) / 256) * n_tiles;
+    const int q = warp & 3, hh = (warp - kEpiWarp0) >> 2;
+    constexpr int kBoxes = kDxBN / 64 / kDx2EW;                  // boxes (and staging buffers) per warp
+    uint8_t* my_stage = sStage + (hh * 4 + q) * kBoxes * kStageWarpBytes;
+    const float gs = (float)((gscale ? (double)gscale[0] : 1.0) / den[0]);
+    uint32_t tn = 0;
+    for (int tile = d.first; tile < total; tile += d.stride, ++tc, ++tn) {
+        const int mt = tile / n_tiles, nt = tile % n_tiles;
+        const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
+        mbar_wait_warp(&t_full[buf], tph);
+        tc_fence_after_sync();
+        const bool tr = trace && tn < 8 && threadIdx.x == kEpiWarp0 * 32;
+        if (tr) trace[blockIdx.x * 64 + tn * 8 + 3] = gtime();
+        const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN + hh * kBoxes * 64);
+        uint32_t v[2 * kBoxes][32];
+        if (!(dbg & 2)) {
+#pragma unroll
+            for (int g = 0; g < 2 * kBoxes; ++g) tmem_ld32(t_row + g * 32, v[g]);
+            tmem_ld_wait();
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_leader(&t_empty[buf]);
+            tma_store_wait_read<0>();                            // last tile's stores have read the staging buffers
+        }
+        __syncwarp();
+        if (F32OUT) {
+            // fp32 dX: the warp's 128 columns are four boxes of 32 floats; two staging buffers, two rounds
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                if (rnd) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
+#pragma unroll
+                for (int b = 0; b < kBoxes; ++b) {
+                    const int g = rnd * kBoxes + b;
+                    uint8_t* sbuf = my_stage + b * kStageWarpBytes;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4 o = make_float4(gs * __uint_as_float(v[g][4 * c]), gs * __uint_as_float(v[g][4 * c + 1]),
+                                               gs * __uint_as_float(v[g][4 * c + 2]), gs * __uint_as_float(v[g][4 * c + 3]));
+                        *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(tm_dx, sbuf, nt * kDxBN + hh * kBoxes * 64 + g * 32, mt * 256 + rank * 128 + q * 32);
+                        tma_store_commit();
+                    }
+                }
+            }
+        } else if (!(dbg & 2)) {
+#pragma unroll
+            for (int b = 0; b < kBoxes; ++b) {
+                uint8_t* sbuf = my_stage + b * kStageWarpBytes;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float g[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[2 * b + h][i]);
+#pragma unroll
+                    for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
+                }
+                // (developer probe: staging without the store gives 5.3 instead of 6.3 us per tile; coalesced LSU stores of the
+                //  staged box instead of TMA give the same 6.3 -- it is the output traffic itself, not the TMA unit)
+                if (dbg & 8) continue;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tm_dx, sbuf, nt * kDxBN + (hh * kBoxes + b) * 64, mt * 256 + rank * 128 + q * 32);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (tr) trace[blockIdx.x * 64 + tn * 8 + 4] = gtime();
+    }
+    if (lane == 0) tma_store_wait_read<0>();      // staging buffers read; the stores land before the grid ends
+}
+
 // =================================================================================================
 // forward: logits in TMEM -> loss, statistics, dZ
 // =================================================================================================
@@ -148,10 +365,21 @@ struct FwdArgs {
     uint2* xch_stats;          // [row block][2][CL][128][6] (value, epoch) words: per-row statistics exchanged between the units of a group
     unsigned int* xch_epoch;   // epochs used so far on this workspace; only grows, so stale words never match
     unsigned int* tile_flags;  // nullable: [row tile][unit * 2 + cta][epilogue warp] "grad-logits landed" words (OSB_FWD_PUBLISH_ROW_TILES)
+    unsigned int* flag_epoch;  // fused forward + dX: launches so far on this workspace; a published word holds 0x80000000 + epoch + 1
     long long* trace;      // optional [gridDim.x][64] clock stamps (developer tool, NULL in production)
 };
 
 constexpr int kStatFloats = 6;          // m, s, zy, sumz, mv, argmax  (per row, per column slice)
+
+// The dX GEMM behind the forward loops of the same kernel (head_fwd_kernel<..., FUSE = true>): its operands and output.
+struct DxFuse {
+    CUtensorMap tm_dz;         // dZ as the K-major A operand (loads)
+    CUtensorMap tm_w;          // W as the MN-major B operand
+    CUtensorMap tm_dx;         // dX (stores)
+    const float* gscale;       // upstream gradient (device scalar) or NULL = 1
+    int dx_f32;                // element type of dX
+    int fwd_units;             // units [0, fwd_units) run the forward; every unit of the grid runs dX tiles
+};
 
 // One CTA owns 128 rows x BN classes of the logits (BN = 128 or 256 TMEM columns, double-buffered so the
 // epilogue of tile t overlaps the MMAs of tile t+1).  Heads wider than BN run as a group of CL = ceil(C/BN)
@@ -222,11 +450,17 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float* f) 
 
 // 10 warps get 168 registers each: the register file is handed out in 4-warp granules, so 320 threads are budgeted as 384
 // (a 200-register build fails to launch).
-template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED, bool PLANES2>
+// FUSE: the grid covers every SM; the units beyond fz.fwd_units skip the forward, and EVERY unit goes on with tiles of the dX
+// GEMM on the same pipeline state (stage ring, TMEM buffers, barriers): the MMA warp issues its first dX tiles while the
+// epilogue warps are still in the forward's last epilogue, and the SMs the forward leaves idle work from the start.  dZ
+// still travels through global memory; the row-tile words (value 0x80000000 + launch epoch + 1) say which rows have landed.
+template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED, bool PLANES2, bool FUSE = false>
 __global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                const __grid_constant__ CUtensorMap tm_dz, const FwdArgs a) {
+                const __grid_constant__ CUtensorMap tm_dz, const FwdArgs a, const __grid_constant__ DxFuse fz) {
     using Cfg = FwdCfg<BN, CL, STAGES, EW, PAIR>;
+    static_assert(!FUSE || (PAIR && BN == kDxBN && Cfg::kStageBytes == kDx2StageBytes && EW == kDx2EW && !WANT_PRED),
+                  "the fused dX phase reuses the forward's stages, staging buffers and TMEM columns as they are");
     constexpr int TM = Cfg::kTileRows;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
@@ -245,11 +479,15 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // strand ~16 of the 148 SMs (GPC packing); it only needs co-residency, which the cooperative launch gives.
     const int cr = PAIR ? (int)cluster_ctarank_() : 0;
     const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units = FUSE ? fz.fwd_units : (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+    const bool in_fwd = !FUSE || unit < n_units;
     const uint32_t rank = (CL > 1) ? (uint32_t)(unit % CL) : 0u;
     const int cluster_id = unit / CL, n_clusters = n_units / CL;
     const int xid = PAIR ? cluster_id * 2 + cr : cluster_id;      // slot of this CTA's rows in the exchange buffers
-    const int n_tiles = (a.B + TM - 1) / TM;
+    const int n_tiles = in_fwd ? (a.B + TM - 1) / TM : 0;         // (a unit outside the forward has no forward tiles)
+    const uint32_t pub_value = FUSE ? (0x80000000u + *a.flag_epoch + 1u) : 1u;
+    DxShape dxs;
+    if (FUSE) { dxs.B = a.B; dxs.K = a.K; dxs.C = a.C; dxs.planes = a.dz_planes; dxs.first = unit; dxs.stride = (int)(gridDim.x >> 1); }
     const int n_kb = (a.K + BK - 1) / BK;
     const int n0 = (int)rank * BN;                        // class range of this unit
     int ncols = a.C - n0;
@@ -261,13 +499,14 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], (PAIR ? 2 : 1) * 4 * EW); }
         fence_barrier_init();
         prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_w); prefetch_tensormap(&tm_dz);
+        if (FUSE) { prefetch_tensormap(&fz.tm_dz); prefetch_tensormap(&fz.tm_w); prefetch_tensormap(&fz.tm_dx); }
     }
     if (HAS_BIAS) {
         for (int i = threadIdx.x; i < BN; i += Cfg::kThreads) sBias[i] = (i < ncols) ? a.bias[n0 + i] : 0.f;
     }
     for (int i = threadIdx.x; i < 2 * BM * 8; i += Cfg::kThreads) sX[i] = make_uint2(0u, 0u);     // epoch 0 = nothing published
     if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
-    if (PAIR && a.tile_flags && warp >= kEpiWarp0 && lane == 0) {
+    if (PAIR && !FUSE && a.tile_flags && warp >= kEpiWarp0 && lane == 0) {
         // every word is cleared by the thread that sets it later, and before this CTA lets the dependent kernel start
         for (int tile = cluster_id; tile < n_tiles; tile += n_clusters)
             a.tile_flags[(size_t)tile * kRowFlagWords + (rank * 2 + cr) * 8 + (warp - kEpiWarp0)] = 0u;
@@ -282,6 +521,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         // (issue loops run warp-converged with one elected lane issuing, see the MMA issuer below)
+        uint32_t it = 0;
         if (ncols > 0) {
             // the first tile has nobody to prefetch it: ask for all of its feature rows at once (the units of the group
             // share the k-blocks), so that HBM latency is paid once and not once per pipeline refill
@@ -289,7 +529,6 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int kb = (int)rank; kb < n_kb; kb += CL) tma_prefetch_l2_2d(&tm_x, kb * BK, cluster_id * TM + cr * BM);
             }
             __syncwarp();
-            uint32_t it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -315,15 +554,16 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 }
             }
         }
+        if constexpr (FUSE) dx_producer<STAGES>(smem, full, empty, it, &fz.tm_dz, &fz.tm_w, dxs, cr, lane, 0, a.tile_flags, pub_value, CL * 2);
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------
         // The whole warp runs the issue loop converged and ONE elected lane issues.  With the loop inside an
         // `if (lane == 0)` region ptxas keeps the descriptors in vector registers and moves five of them to uniform
         // registers (ELECT + R2UR.BROADCAST) before every MMA: 143..182 cycles per MMA measured, more than the
         // 128 cycles the tensor pipe needs (tools/mma_rate_probe.cu).
+        uint32_t it = 0, tc = 0;
         if (ncols > 0 && cr == 0) {
             const uint32_t idesc = make_idesc_bf16(TM, ncolsN, false, false);
-            uint32_t it = 0, tc = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tc) {
                 const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
                 mbar_wait(&t_empty[buf], tph ^ 1);
@@ -352,6 +592,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 if (a.trace && tc < 4 && lane == 0) a.trace[blockIdx.x * 64 + tc * 8 + 2] = gtime();
             }
         }
+        if constexpr (FUSE) {
+            if (cr == 0) dx_mma<STAGES>(smem, full, empty, t_full, t_empty, it, tc, tbase, dxs, lane, nullptr);
+            __syncwarp();
+        }
     } else {
         // ------------------------------ epilogue ----------------------------------
         // warp (q, h): TMEM lane quadrant q = warp % 4 (hardware rule), column slice h; one thread per row.
@@ -371,7 +615,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tma_store_wait<0>();                         // in global memory, not merely read out of shared memory
                 __threadfence();
                 asm volatile("st.release.gpu.global.u32 [%0], %1;"
-                             :: "l"(a.tile_flags + (size_t)pub_tile * kRowFlagWords + (rank * 2 + cr) * 8 + (warp - kEpiWarp0)), "r"(1u) : "memory");
+                             :: "l"(a.tile_flags + (size_t)pub_tile * kRowFlagWords + (rank * 2 + cr) * 8 + (warp - kEpiWarp0)), "r"(pub_value) : "memory");
             }
             pub_tile = -1;
         };
@@ -657,7 +901,8 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         //      all partials in index order (lane l takes l, l + 32, ...; fixed shuffle tree on top) ----
         const bool trx = a.trace && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32;
         if (trx) a.trace[256 * 64 + 192 + 0] = gtime();
-        if (rank == 0 && h == 0) {
+        if (FUSE) publish();                              // the dX tiles of every pair wait for these rows: publish them now
+        if (in_fwd && rank == 0 && h == 0) {
             const unsigned n_part = (unsigned)n_clusters * (PAIR ? 2u : 1u) * 4u;
             const double wl = warp_sum(loss_acc);
             unsigned last = 0;
@@ -678,11 +923,17 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     a.loss[0] = a.den ? (float)(tot / a.den[0]) : (float)tot;
                     *a.ticket = 0u;
                     if (CL > 1) *a.xch_epoch = ep_base + (uint32_t)((n_tiles + n_clusters - 1) / n_clusters) + 1u;
+                    if (FUSE) *a.flag_epoch = pub_value - 0x80000000u;      // every CTA read the old value when it started
                 }
             }
         }
         publish();                                        // the last tile of this CTA (after the loss reduction: this one does wait)
         if (lane == 0) tma_store_wait_read<0>();          // the staging buffers have been read; the data lands before the grid ends
+        if constexpr (FUSE) {
+            __syncwarp();
+            if (fz.dx_f32) dx_epilogue<true>(sDz, t_full, t_empty, it, tbase, &fz.tm_dx, dxs, cr, warp, lane, fz.gscale, a.den, nullptr, 0);
+            else dx_epilogue<false>(sDz, t_full, t_empty, it, tbase, &fz.tm_dx, dxs, cr, warp, lane, fz.gscale, a.den, nullptr, 0);
+        }
         if (trx) a.trace[256 * 64 + 192 + 1] = gtime();
     }
     if (a.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) a.trace[256 * 64 + 200 + warp] = gtime();
@@ -692,24 +943,6 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (warp == 1) { if (PAIR) tmem_dealloc2(tbase, Cfg::kTmemCols); else tmem_dealloc(tbase, Cfg::kTmemCols); }
     if (a.trace && threadIdx.x == 0) a.trace[(384 + blockIdx.x / 32) * 64 + (blockIdx.x % 32) * 2 + 1] = gtime();
 }
-
-constexpr int kDxBN = 256;
-// =================================================================================================
-// dX = g * dZ W with CTA pairs (cta_group::2): A = dZ tile (K-major over classes), B = W tile viewed MN-major (N = feature
-// index); one cluster of 2 CTAs per 256 rows x 256 features, M = 256 MMAs.  The K loop runs over the classes of every dZ
-// plane (plane 1 = rounding residual of plane 0, the W k-block is the same).
-// CTA r of the pair loads rows [128 r, +128) of the dZ tile and features [128 r, +128) of the W tile (32 KB per stage
-// instead of 48 KB), the leader issues the MMAs, each CTA drains its own 128 x 256 accumulator from its TMEM.
-// =================================================================================================
-// kDx2EW warps per TMEM lane quadrant drain the accumulator.
-constexpr int kDx2EW = 2;
-constexpr int kDx2Threads = (2 + 4 * kDx2EW) * 32;
-constexpr int kDx2Stages = 5;
-constexpr int kDx2StageBytes = kABytes + 2 * kBoxBytes;         // 32 KB per CTA
-constexpr int kDx2OffStage = kDx2Stages * kDx2StageBytes;
-constexpr int kDx2OffBars = kDx2OffStage + 4 * (kDxBN / 64) * kStageWarpBytes;      // one staging buffer per (quadrant, 64-column box)
-constexpr int kDx2SmemBytes = kDx2OffBars + (2 * kDx2Stages + 4) * 8 + 16 + 1024;
-static_assert(kDx2SmemBytes <= 232448, "dx2 kernel shared memory");
 
 template <bool F32OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDx2Threads, 1)
@@ -733,7 +966,6 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank_();
-    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kDx2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 2 * 4 * kDx2EW); }     // epilogue warps x 2 CTAs
@@ -747,146 +979,20 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
     pdl_wait();                 // dZ comes from the kernel in front of this one
     pdl_trigger();
     const uint32_t tbase = *tmem_slot;
-    const int m_tiles = (B + 255) / 256, n_tiles = (K + kDxBN - 1) / kDxBN;
-    const int total = m_tiles * n_tiles;
-    const int n_kb1 = (C + BK - 1) / BK;            // k-blocks of one plane
-    const int n_kb = n_kb1 * planes;
-
+    DxShape d;
+    d.B = B; d.K = K; d.C = C; d.planes = planes; d.first = (int)(blockIdx.x >> 1); d.stride = (int)(gridDim.x >> 1);
     if (warp == 0) {
         uint32_t it = 0;
-        for (int tile = pair; tile < total; tile += n_pairs) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                const int pl = kb >= n_kb1 ? 1 : 0, kc = kb - pl * n_kb1;
-                const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * kDx2StageBytes;
-                if (elect_one()) {
-                    if ((dbg & 1) && it >= kDx2Stages) {        // developer probe: MMA rate without operand traffic (stale tiles)
-                        if (rank == 0) mbar_arrive(&full[s]);
-                    } else {
-                        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDx2StageBytes);     // both CTAs' bytes land on the leader's barrier
-                        tma_load_3d_2sm(st, &tm_dz, &full[s], kc * BK, mt * 256 + rank * 128, pl);            // 64 classes x 128 rows
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)                                                         // 64 features x 64 classes
-                            tma_load_2d_2sm(st + kABytes + j * kBoxBytes, &tm_w, &full[s], nt * kDxBN + rank * 128 + j * 64, kc * BK);
-                    }
-                }
-                __syncwarp();
-            }
-        }
+        dx_producer<kDx2Stages>(smem, full, empty, it, &tm_dz, &tm_w, d, rank, lane, dbg, nullptr, 0u, 0);
     } else if (warp == 1) {
         if (rank == 0) {
-            const uint32_t idesc = make_idesc_bf16(256, kDxBN, false, true);
             uint32_t it = 0, tc = 0;
-            for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
-                const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-                mbar_wait(&t_empty[buf], tph ^ 1);
-                tc_fence_after_sync();
-                if (trace && tc < 8 && lane == 0) { trace[blockIdx.x * 64 + tc * 8 + 0] = gtime(); trace[blockIdx.x * 64 + tc * 8 + 7] = clock64(); }
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const uint32_t s = it % kDx2Stages, ph = (it / kDx2Stages) & 1;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after_sync();
-                    if (trace && blockIdx.x == 0 && tc >= 1 && tc < 3 && lane == 0) trace[256 * 64 + (tc - 1) * 32 + kb] = clock64();
-                    const uint32_t a_addr = smem_u32(smem + s * kDx2StageBytes);
-                    const uint64_t adesc = make_desc_kmajor(a_addr), bdesc = make_desc_mnmajor(a_addr + kABytes, kBoxBytes);
-                    const int rem = C - (kb >= n_kb1 ? kb - n_kb1 : kb) * BK;
-                    const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            if (k < ksteps) umma2_bf16(tbase + buf * kDxBN, adesc + 2 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
-                        umma2_commit_mc(&empty[s]);
-                        if (kb == n_kb - 1) umma2_commit_mc(&t_full[buf]);
-                    }
-                    __syncwarp();
-                }
-                if (trace && tc < 8 && lane == 0) trace[blockIdx.x * 64 + tc * 8 + 2] = gtime();
-            }
+            dx_mma<kDx2Stages>(smem, full, empty, t_full, t_empty, it, tc, tbase, d, lane, trace);
         }
         __syncwarp();
     } else {
-        // warp (q, hh): lane quadrant q, column half hh.  A thread pulls its 128 accumulator columns into registers with one
-        // TMEM sweep and hands the buffer back to the MMA warp at once; conversion, staging and the TMA stores run after
-        // that.  Every 64-column box has its own staging buffer, so nothing waits for a store issued in the same tile
-        // (with two buffers per warp and four boxes per tile the drain waited ~0.5 us per box for the store two boxes
-        // back to finish reading, 4.5 us per tile against 5.3 us of MMAs).
-        const int q = warp & 3, hh = (warp - kEpiWarp0) >> 2;
-        constexpr int kBoxes = kDxBN / 64 / kDx2EW;                  // boxes (and staging buffers) per warp
-        uint8_t* my_stage = sStage + (hh * 4 + q) * kBoxes * kStageWarpBytes;
-        const float gs = (float)((gscale ? (double)gscale[0] : 1.0) / den[0]);
         uint32_t tc = 0;
-        for (int tile = pair; tile < total; tile += n_pairs, ++tc) {
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
-            const uint32_t buf = tc & 1, tph = (tc >> 1) & 1;
-            mbar_wait_warp(&t_full[buf], tph);
-            tc_fence_after_sync();
-            const bool tr = trace && tc < 8 && threadIdx.x == kEpiWarp0 * 32;
-            if (tr) trace[blockIdx.x * 64 + tc * 8 + 3] = gtime();
-            const uint32_t t_row = tmem_addr(tbase, q * 32, buf * kDxBN + hh * kBoxes * 64);
-            uint32_t v[2 * kBoxes][32];
-            if (!(dbg & 2)) {
-#pragma unroll
-                for (int g = 0; g < 2 * kBoxes; ++g) tmem_ld32(t_row + g * 32, v[g]);
-                tmem_ld_wait();
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_leader(&t_empty[buf]);
-                tma_store_wait_read<0>();                            // last tile's stores have read the staging buffers
-            }
-            __syncwarp();
-            if (F32OUT) {
-                // fp32 dX: the warp's 128 columns are four boxes of 32 floats; two staging buffers, two rounds
-#pragma unroll
-                for (int rnd = 0; rnd < 2; ++rnd) {
-                    if (rnd) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }
-#pragma unroll
-                    for (int b = 0; b < kBoxes; ++b) {
-                        const int g = rnd * kBoxes + b;
-                        uint8_t* sbuf = my_stage + b * kStageWarpBytes;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            float4 o = make_float4(gs * __uint_as_float(v[g][4 * c]), gs * __uint_as_float(v[g][4 * c + 1]),
-                                                   gs * __uint_as_float(v[g][4 * c + 2]), gs * __uint_as_float(v[g][4 * c + 3]));
-                            *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tm_dx, sbuf, nt * kDxBN + hh * kBoxes * 64 + g * 32, mt * 256 + rank * 128 + q * 32);
-                            tma_store_commit();
-                        }
-                    }
-                }
-            } else if (!(dbg & 2)) {
-#pragma unroll
-                for (int b = 0; b < kBoxes; ++b) {
-                    uint8_t* sbuf = my_stage + b * kStageWarpBytes;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float g[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) g[i] = gs * __uint_as_float(v[2 * b + h][i]);
-#pragma unroll
-                        for (int cch = 0; cch < 4; ++cch) stage_chunk(sbuf, lane, h * 4 + cch, g + cch * 8);
-                    }
-                    // (developer probe: staging without the store gives 5.3 instead of 6.3 us per tile; coalesced LSU stores of the
-                    //  staged box instead of TMA give the same 6.3 -- it is the output traffic itself, not the TMA unit)
-                    if (dbg & 8) continue;
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tm_dx, sbuf, nt * kDxBN + (hh * kBoxes + b) * 64, mt * 256 + rank * 128 + q * 32);
-                        tma_store_commit();
-                    }
-                }
-            }
-            if (tr) trace[blockIdx.x * 64 + tc * 8 + 4] = gtime();
-        }
-        if (lane == 0) tma_store_wait_read<0>();      // staging buffers read; the stores land before the grid ends
+        dx_epilogue<F32OUT>(sStage, t_full, t_empty, tc, tbase, &tm_dx, d, rank, warp, lane, gscale, den, trace, dbg);
     }
     tc_fence_before_sync();
     cluster_sync_();
@@ -1053,39 +1159,9 @@ head_dw2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const uint32_t s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
             const int pl = kb >= kb_rows ? 1 : 0, kr = kb - pl * kb_rows;
-            if (row_flags) {
-                const int rt = (kr * BK) / kRowFlagTileRows;
-                if (rt < ready_lo || rt >= ready_hi) {
-                    // lanes 8j .. 8j+7 look at the (up to) 8 slots x 8 warp words of row tile rt + j: four tiles per poll
-                    const int j = rt + (lane >> 3), slot = lane & 7;
-                    const bool mine = j < n_row_tiles && slot < row_flag_slots;
-                    const unsigned int* fp = row_flags + ((size_t)j * 8 + slot) * 8;
-                    const long long t0 = gtime();
-                    unsigned got;
-                    for (;;) {
-                        bool ok = true;
-                        if (mine) {
-                            uint32_t f[8];
-                            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]) : "l"(fp) : "memory");
-                            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]) : "l"(fp + 4) : "memory");
-                            ok = (f[0] & f[1] & f[2] & f[3] & f[4] & f[5] & f[6] & f[7]) != 0u;
-                        }
-                        got = __ballot_sync(0xffffffffu, ok);
-                        if ((got & 0xffu) == 0xffu) break;
-                        if (__any_sync(0xffffffffu, gtime() - t0 > 500000000LL)) {   // not behind a publishing forward after all: plain dependency
-                            pdl_wait();
-                            got = 0xffffffffu; ready_lo = -(1 << 30);
-                            break;
-                        }
-                        __nanosleep(256);
-                    }
-                    __threadfence();                            // acquire side of the flags' release
-                    asm volatile("fence.proxy.async;" ::: "memory");    // the loads that follow are TMA (async proxy) reads
-                    int n = 1;
-                    while (n < 4 && ((got >> (8 * n)) & 0xffu) == 0xffu) ++n;
-                    if (ready_lo < 0) { ready_lo = 0; ready_hi = 1 << 30; }
-                    else { ready_lo = rt; ready_hi = rt + n; }
-                }
+            if (row_flags && !wait_row_tiles(row_flags, 1u, (kr * BK) / kRowFlagTileRows, n_row_tiles, row_flag_slots, lane, ready_lo, ready_hi)) {
+                pdl_wait();                                     // not behind a publishing forward after all: plain dependency
+                ready_lo = 0; ready_hi = 1 << 30;
             }
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + s * kDw2StageBytes;
@@ -1586,13 +1662,13 @@ static int set_smem(KernelT kernel, int bytes) {
     return OSB_OK;
 }
 
-template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED, bool PLANES2>
+template <int BN, int CL, int STAGES, int EW, bool PAIR, bool HAS_BIAS, bool WANT_PRED, bool PLANES2, bool FUSE = false>
 static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
-                        int max_ctas, cudaStream_t st) {
+                        int max_ctas, cudaStream_t st, const DxFuse* fuse = nullptr) {
     using Cfg = FwdCfg<BN, CL, STAGES, EW, PAIR>;
     constexpr int kCtasPerGroup = CL * (PAIR ? 2 : 1);
     const int n_tiles = (a.B + Cfg::kTileRows - 1) / Cfg::kTileRows;
-    auto k = head_fwd_kernel<BN, CL, STAGES, EW, PAIR, HAS_BIAS, WANT_PRED, PLANES2>;
+    auto k = head_fwd_kernel<BN, CL, STAGES, EW, PAIR, HAS_BIAS, WANT_PRED, PLANES2, FUSE>;
     int rc = set_smem(k, Cfg::kSmemBytes); if (rc) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -1619,8 +1695,29 @@ static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
     const int rounds = (n_tiles + groups - 1) / groups;
     groups = (n_tiles + rounds - 1) / rounds;
     cfg.gridDim = dim3(groups * kCtasPerGroup);
-    OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a));
+    DxFuse fz;
+    if (FUSE) {
+        // every SM: the units beyond the forward's groups start with dX tiles at once
+        fz = *fuse;
+        fz.fwd_units = groups * CL;
+        cfg.gridDim = dim3((unsigned)(cta_limit(max_ctas) / 2 * 2));
+        if (cfg.gridDim.x < (unsigned)(groups * kCtasPerGroup)) cfg.gridDim = dim3(groups * kCtasPerGroup);
+    } else {
+        memset(&fz, 0, sizeof(fz));
+    }
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, k, tx, tw, tdz, a, fz));
     return OSB_OK;
+}
+
+// the fused forward + dX kernel: 256-column units only, no per-row predictions (a training step does not read them)
+template <int CL>
+static int launch_fwd_dx(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tdz, const FwdArgs& a,
+                         int max_ctas, cudaStream_t st, const DxFuse& fuse) {
+    const bool two = a.dz_planes > 1;
+#define OSB_FWDX(BIAS_) (two ? launch_fwd_k<256, CL, 4, 2, true, BIAS_, false, true, true>(tx, tw, tdz, a, max_ctas, st, &fuse) \
+                             : launch_fwd_k<256, CL, 4, 2, true, BIAS_, false, false, true>(tx, tw, tdz, a, max_ctas, st, &fuse))
+    return a.bias ? OSB_FWDX(true) : OSB_FWDX(false);
+#undef OSB_FWDX
 }
 
 template <int BN, int CL, int STAGES>
@@ -1731,14 +1828,16 @@ static int check_head_shapes(const char* fn, int64_t B, int K, int C, int64_t ld
     return OSB_OK;
 }
 
-extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
-                                const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
-                                int64_t ignore_index, const double* den, int valid_cols,
-                                double* loss_num, float* loss,
-                                float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
-                                void* dz, int64_t lddz, int dz_planes, int flags, int max_ctas,
-                                void* ws, size_t ws_bytes, void* stream) {
-    OSB_ENTRY_GUARD();
+// what osb_head_forward_dx adds to a forward call
+struct FuseDxRequest { const float* gscale; void* dx; int64_t lddx; int dx_dtype; };
+
+static int head_forward_impl(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
+                             const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
+                             int64_t ignore_index, const double* den, int valid_cols,
+                             double* loss_num, float* loss,
+                             float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
+                             void* dz, int64_t lddz, int dz_planes, int flags, int max_ctas,
+                             void* ws, size_t ws_bytes, void* stream, const FuseDxRequest* fuse, bool* fused_out) {
     OSB_REQUIRE(x && w && y && loss_num && loss && ws, OSB_ERR_ARG, "osb_head_forward: null pointer");
     int rc = check_head_shapes("osb_head_forward", B, K, C, ldx);
     if (rc) return rc;
@@ -1777,6 +1876,28 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     a.trace = g_trace;
     a.tile_flags = ((flags & OSB_FWD_PUBLISH_ROW_TILES) && dz && row_flags_usable(B, K, C))
                        ? reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffRowFlags) : nullptr;
+    a.flag_epoch = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffFlagEpoch);
+    if (fused_out) *fused_out = false;
+    // forward + dX as ONE kernel: persistent 256-column units (heads wider than 128 classes, batches the split-K kernel
+    // does not take), grad-logits and a denominator present, row-tile words for the whole batch
+    static const bool no_fuse = getenv("OSB_NO_FUSED_DX") != nullptr;            // developer A/B switch
+    if (fuse && !no_fuse && !splitk && C > BM && dz && den && !row_pred && !row_pmax_all &&
+        (B + kRowFlagTileRows - 1) / kRowFlagTileRows <= kMaxRowFlagTiles) {
+        DxFuse fz;
+        memset(&fz, 0, sizeof(fz));
+        OSB_TMAP(make_tmap_bf16_3d(&fz.tm_dz, dz, (uint64_t)dz_planes, (uint64_t)B, (uint64_t)C, (uint64_t)lddz, (uint64_t)B * (uint64_t)lddz, BM), "dz (K-major)");
+        OSB_TMAP(make_tmap_bf16(&fz.tm_w, w, (uint64_t)C, (uint64_t)K, (uint64_t)K, 64), "w (MN-major)");
+        if (fuse->dx_dtype == OSB_F32) OSB_TMAP(make_tmap_f32_2d(&fz.tm_dx, fuse->dx, (uint64_t)B, (uint64_t)K, (uint64_t)fuse->lddx, 32), "dx (fp32)");
+        else OSB_TMAP(make_tmap_bf16(&fz.tm_dx, fuse->dx, (uint64_t)B, (uint64_t)K, (uint64_t)fuse->lddx, 32), "dx");
+        fz.gscale = fuse->gscale;
+        fz.dx_f32 = fuse->dx_dtype == OSB_F32 ? 1 : 0;
+        a.tile_flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + kWsOffRowFlags);
+        if (fused_out) *fused_out = true;
+        if (C <= 256) return launch_fwd_dx<1>(tx, tw, tdz, a, max_ctas, st, fz);
+        if (C <= 512) return launch_fwd_dx<2>(tx, tw, tdz, a, max_ctas, st, fz);
+        if (C <= 768) return launch_fwd_dx<3>(tx, tw, tdz, a, max_ctas, st, fz);
+        return launch_fwd_dx<4>(tx, tw, tdz, a, max_ctas, st, fz);
+    }
     if (splitk) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)((B + BM - 1) / BM) * kSkS);
@@ -1806,6 +1927,46 @@ extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const
     if (C <= 512) return launch_fwd<256, 2, 4>(tx, tw, tdz, a, max_ctas, st);
     if (C <= 768) return launch_fwd<256, 3, 4>(tx, tw, tdz, a, max_ctas, st);
     return launch_fwd<256, 4, 4>(tx, tw, tdz, a, max_ctas, st);
+}
+
+extern "C" int osb_head_forward(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
+                                const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
+                                int64_t ignore_index, const double* den, int valid_cols,
+                                double* loss_num, float* loss,
+                                float* row_ptgt, float* row_pmax, float* row_pmax_all, int32_t* row_pred,
+                                void* dz, int64_t lddz, int dz_planes, int flags, int max_ctas,
+                                void* ws, size_t ws_bytes, void* stream) {
+    OSB_ENTRY_GUARD();
+    return head_forward_impl(x, ldx, w, bias, y, class_w, B, K, C, variant, unk_weight, ignore_index, den, valid_cols, loss_num, loss,
+                             row_ptgt, row_pmax, row_pmax_all, row_pred, dz, lddz, dz_planes, flags, max_ctas, ws, ws_bytes, stream,
+                             nullptr, nullptr);
+}
+
+// forward + dX of a training step in one call; ONE kernel where the shape allows (osb_head_forward_dx_is_fused), else the
+// forward kernel and the dX GEMM one after the other -- the same bits either way
+extern "C" int osb_head_forward_dx(const void* x, int64_t ldx, const void* w, const float* bias, const int64_t* y,
+                                   const float* class_w, int64_t B, int K, int C, int variant, double unk_weight,
+                                   int64_t ignore_index, const double* den, int valid_cols,
+                                   double* loss_num, float* loss, float* row_ptgt, float* row_pmax,
+                                   void* dz, int64_t lddz, int dz_planes, const float* gscale,
+                                   void* dx, int64_t lddx, int dx_dtype, int flags, int max_ctas,
+                                   void* ws, size_t ws_bytes, void* stream) {
+    OSB_ENTRY_GUARD();
+    OSB_REQUIRE(dz && dx && den, OSB_ERR_ARG, "osb_head_forward_dx: dz, dx and den are required");
+    OSB_REQUIRE(dx_dtype == OSB_BF16 || dx_dtype == OSB_F32, OSB_ERR_ARG, "osb_head_forward_dx: bad dx_dtype %d", dx_dtype);
+    OSB_REQUIRE(lddx >= K && lddx % 8 == 0 && (uintptr_t)dx % 16 == 0, OSB_ERR_ARG, "osb_head_forward_dx: bad dx / lddx=%lld", (long long)lddx);
+    FuseDxRequest rq{gscale, dx, lddx, dx_dtype};
+    bool fused = false;
+    int rc = head_forward_impl(x, ldx, w, bias, y, class_w, B, K, C, variant, unk_weight, ignore_index, den, valid_cols, loss_num, loss,
+                               row_ptgt, row_pmax, nullptr, nullptr, dz, lddz, dz_planes, flags, max_ctas, ws, ws_bytes, stream, &rq, &fused);
+    if (rc || fused) return rc;
+    return osb_head_backward(dz, lddz, dz_planes, den, x, ldx, w, B, K, C, gscale, dx, lddx, dx_dtype, nullptr, nullptr, max_ctas, 0,
+                             ws, ws_bytes, stream);
+}
+extern "C" int osb_head_forward_dx_is_fused(int64_t B, int K, int C) {
+    if (osb::check_device() != OSB_OK) return 0;
+    static const bool no_fuse = getenv("OSB_NO_FUSED_DX") != nullptr;
+    return (!no_fuse && !fwd_use_splitk(B, K, C, 0) && C > BM && (B + kRowFlagTileRows - 1) / kRowFlagTileRows <= kMaxRowFlagTiles) ? 1 : 0;
 }
 
 // the dW GEMM (split-K partials into the workspace); returns the split count through *splits_out

@@ -91,8 +91,11 @@ class HeadPlan:
         self.dw = self.flat[:C * K].view(C, K)
         self.db = self.flat[C * K:C * K + C] if bias else None
         self.dw_direct = bool(L.size("osb_head_dw_is_direct", B, K, C))
-        # label_stats, fwd, dx, dw (+ the split-K reduce unless the GEMM writes dW directly) (+ db)
+        self.fused_dx = bool(L.size("osb_head_forward_dx_is_fused", B, K, C))
+        # label_stats, fwd, dx, dw (+ the split-K reduce unless the GEMM writes dW directly) (+ db); a captured step runs
+        # forward and dX as one kernel where the shape allows
         self.launches_per_step = 4 + (0 if self.dw_direct else 1) + (1 if bias else 0)
+        self.launches_per_captured_step = self.launches_per_step        # set by capture()
 
     @property
     def den_step(self) -> torch.Tensor:
@@ -126,6 +129,17 @@ class HeadPlan:
                L.ptr(self.dz) if write_dz else None, self.lddz, self.planes, int(flags), int(max_ctas),
                L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
+    def forward_dx(self, x, w, y, bias=None, gscale=None, den="step", flags=0, max_ctas=0):
+        """Forward and dX of a training step from ONE call (``osb_head_forward_dx``): one kernel where ``self.fused_dx``,
+        whose CTA pairs go on with dX tiles under the forward's last epilogue; no per-row predictions."""
+        if isinstance(den, str):
+            den = self.den_step
+        L.call("osb_head_forward_dx", L.ptr(x), self.K, L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(self.class_w),
+               self.B, self.K, self.C, self.variant, self.unk_weight, self.ignore_index, L.ptr(den), self.valid_cols,
+               L.ptr(self.loss_num), L.ptr(self.loss), L.ptr(self.p_target), L.ptr(self.p_max),
+               L.ptr(self.dz), self.lddz, self.planes, L.ptr(gscale), L.ptr(self.dx), self.K, self._dx_code(),
+               int(flags), int(max_ctas), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
+
     def _dx_code(self):
         return L.F32 if self.dx_dtype == torch.float32 else L.BF16
 
@@ -155,7 +169,7 @@ class HeadPlan:
         L.call("osb_head_backward_dw_partials", L.ptr(self.dz), self.lddz, self.planes, L.ptr(x), self.K, self.B, self.K, self.C,
                L.ptr(self.db), 1 if local_reduce else 0, int(flags), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
-    def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None, handover=False):
+    def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None, handover=False, fused_dx=True):
         """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five
         kernels on the CURRENT CONTENTS of those tensors with a single launch call.  The small-batch configurations
         (B <= 1024) are bound by launch latency, not by the kernels, so this is the path to use in a training loop."""
@@ -185,12 +199,22 @@ class HeadPlan:
             with torch.cuda.stream(lbranch):
                 self.label_stats(y, max_ctas=8)
 
+        # Large batches (serial order): forward and dX as ONE kernel where the shape allows.  Neutral to -3.5 % at 8192 rows
+        # and more, slower below (tools/fused_shapes.py), where the parallel branches are the default anyway.
+        fuse = self.fused_dx and not fork and fused_dx
+        self.launches_per_captured_step = self.launches_per_step - (1 if fuse else 0)
+
         def body():
             if not side_labels:
                 # the forward kernel runs under the label statistics it follows and waits for them only before it
                 # divides the loss (OSB_FWD_DEN_FROM_PREV_KERNEL); the grad-logits do not depend on the denominator
                 self.label_stats(y)
-                self.forward(x, w, y, bias, want_pred=False, flags=L.FWD_DEN_FROM_PREV_KERNEL | pub)
+                if fuse:
+                    self.forward_dx(x, w, y, bias, gscale, flags=L.FWD_DEN_FROM_PREV_KERNEL)
+                else:
+                    self.forward(x, w, y, bias, want_pred=False, flags=L.FWD_DEN_FROM_PREV_KERNEL | pub)
+            elif fuse:
+                self.forward_dx(x, w, y, bias, gscale)
             else:
                 self.forward(x, w, y, bias, want_pred=False, flags=pub)
             if fork:
@@ -213,7 +237,10 @@ class HeadPlan:
             else:
                 if side_labels:
                     labels_beside()
-                self.backward(x, w, gscale)
+                if fuse:
+                    self.backward_dw(x, w, gscale)          # dX came out of the forward's kernel
+                else:
+                    self.backward(x, w, gscale)
             if side_labels:
                 side.wait_stream(lbranch)
 

@@ -383,6 +383,50 @@ def test_head_backward_handover_flag_without_a_publishing_forward_falls_back():
     assert torch.equal(plan.dw, ref)
 
 
+@pytest.mark.parametrize("B,K,C,variant,precision,dx_dtype", [
+    (16384, 2048, 1000, "entropic", "fast", torch.bfloat16),      # the benchmarked step
+    (300, 256, 300, "entropic", "exact", torch.float32),          # 2 row tiles: 72 of the 74 CTA pairs only run dX tiles
+    (5000, 512, 600, "garbage", "exact", torch.bfloat16),         # 3 class slices, ragged last row tile, denominator from the label statistics
+    (2100, 256, 1000, "entropic", "fast", torch.float32),
+    (700, 2048, 152, "softmax", "exact", torch.float32),          # one class slice (no statistics exchange)
+])
+def test_head_forward_dx_fused_matches_two_kernels(B, K, C, variant, precision, dx_dtype):
+    """osb_head_forward_dx runs the forward and the dX GEMM as ONE kernel where the shape allows (every CTA pair goes on
+    with dX tiles on the forward's pipeline state; the pairs the forward leaves idle start with them at once and take the
+    rows of dZ as they are published).  Loss, per-row outputs, dZ and dX must be the bits of forward + backward_dx."""
+    from openset_imagenet_b200.functional import HeadPlan
+    from openset_imagenet_b200 import _lib as L
+    dev = torch.device(DEV)
+    g = torch.Generator(device=dev).manual_seed(B + C)
+    x = torch.randn(B, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(C, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    kw = dict(device=dev, precision=precision, dx_dtype=dx_dtype)
+    if variant == "garbage":
+        yn = O.make_labels(B, C - 1, 1 / 3, seed=3, neg_label=C - 1)
+        kw.update(class_weights=torch.tensor(O.class_weights_from_labels(np.concatenate([yn, np.arange(C)]), C), device=dev), last_valid_class=-1)
+    elif variant == "softmax":
+        yn = O.make_labels(B, C, 0.25, seed=3)
+    else:
+        yn = O.make_labels(B, C, 1 / 3, seed=3)
+    y = torch.tensor(yn, device=dev)
+    plan = HeadPlan(B, K, C, variant, **kw)
+    assert plan.fused_dx == (not bool(L.size("osb_head_forward_is_splitk", B, K, C)) and C > 128)
+    gs = torch.full((1,), 0.75, device=dev)
+    plan.label_stats(y)
+    plan.forward(x, w, y, want_pred=False)
+    plan.backward_dx(x, w, gs)
+    torch.cuda.synchronize()
+    outs = lambda: (plan.loss, plan.loss_num, plan.dz, plan.dx, plan.p_target, plan.p_max)
+    ref = [t.clone() for t in outs()]
+    for rep in range(3):                          # the launch epoch of the row-tile words advances with every call
+        for t in outs():
+            t.zero_()
+        plan.forward_dx(x, w, y, gscale=gs)
+        torch.cuda.synchronize()
+        for got, want in zip(outs(), ref):
+            assert torch.equal(got, want), rep
+
+
 def test_head_bg_protocol_shape_vs_oracle():
     """BASELINE.json's garbage-class configuration (Protocol 3 shape, 151 + 1 classes, 1024 x 2048 per GPU, bias off as in
     train.py:350-352), as bench.py --workload bg runs it: split-K forward, CUDA-graph replay."""
