@@ -269,13 +269,12 @@ __device__ __forceinline__ void dx_mma(uint8_t* smem, uint64_t* full, uint64_t* 
 // (with two buffers per warp and four boxes per tile the drain waited ~0.5 us per box for the store two boxes
 // back to finish reading, 4.5 us per tile against 5.3 us of MMAs).
 template <bool F32OUT>
-__device__ __forceinline__ void dx_epilogue(uint8_t* sStage, uint64_t* t_full, uint64_t* t_empty, uint32_t& tc, uint32_t tbase,
+__device__ __forceinline__ void dx_epilogue(uint8_t* my_stage, uint64_t* t_full, uint64_t* t_empty, uint32_t& tc, uint32_t tbase,
                                             const CUtensorMap* tm_dx, const DxShape& d, int rank, int warp, int lane,
                                             const float* gscale, const double* den, long long* trace, int dbg) {
     const int n_tiles = (d.K + kDxBN - 1) / kDxBN, total = ((d.B + 255) / 256) * n_tiles;
     const int q = warp & 3, hh = (warp - kEpiWarp0) >> 2;
-    constexpr int kBoxes = kDxBN / 64 / kDx2EW;                  // boxes (and staging buffers) per warp
-    uint8_t* my_stage = sStage + (hh * 4 + q) * kBoxes * kStageWarpBytes;
+    constexpr int kBoxes = kDxBN / 64 / kDx2EW;                  // boxes (and staging buffers) per warp: my_stage holds that many
     const float gs = (float)((gscale ? (double)gscale[0] : 1.0) / den[0]);
     uint32_t tn = 0;
     for (int tile = d.first; tile < total; tile += d.stride, ++tc, ++tn) {
@@ -931,8 +930,9 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         if (lane == 0) tma_store_wait_read<0>();          // the staging buffers have been read; the data lands before the grid ends
         if constexpr (FUSE) {
             __syncwarp();
-            if (fz.dx_f32) dx_epilogue<true>(sDz, t_full, t_empty, it, tbase, &fz.tm_dx, dxs, cr, warp, lane, fz.gscale, a.den, nullptr, 0);
-            else dx_epilogue<false>(sDz, t_full, t_empty, it, tbase, &fz.tm_dx, dxs, cr, warp, lane, fz.gscale, a.den, nullptr, 0);
+            // (the warp keeps ITS staging buffers: the wait above covers only the stores this warp issued)
+            if (fz.dx_f32) dx_epilogue<true>(my_stage, t_full, t_empty, it, tbase, &fz.tm_dx, dxs, cr, warp, lane, fz.gscale, a.den, nullptr, 0);
+            else dx_epilogue<false>(my_stage, t_full, t_empty, it, tbase, &fz.tm_dx, dxs, cr, warp, lane, fz.gscale, a.den, nullptr, 0);
         }
         if (trx) a.trace[256 * 64 + 192 + 1] = gtime();
     }
@@ -992,7 +992,8 @@ head_dx2_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant
         __syncwarp();
     } else {
         uint32_t tc = 0;
-        dx_epilogue<F32OUT>(sStage, t_full, t_empty, tc, tbase, &tm_dx, d, rank, warp, lane, gscale, den, trace, dbg);
+        dx_epilogue<F32OUT>(sStage + (warp - kEpiWarp0) * 2 * kStageWarpBytes, t_full, t_empty, tc, tbase, &tm_dx, d, rank, warp, lane,
+                            gscale, den, trace, dbg);
     }
     tc_fence_before_sync();
     cluster_sync_();

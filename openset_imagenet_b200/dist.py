@@ -258,6 +258,7 @@ class ShardedHeadPlan:
                            else torch.zeros(1, dtype=torch.float64, device=dev))
         self._lbranch = torch.cuda.Stream(device=dev)
         self._abranch = torch.cuda.Stream(device=dev)
+        self.fused_step = self.world == 1 and self.plan.fused_dx and self.plan.B > 4096      # as HeadPlan.capture decides
         # our kernels per step: label statistics, forward, dW GEMM, dX, and the split-K reduce (NCCL path) or the peer
         # all-reduce that replaces it (+ the denominator's peer sum for softmax / garbage, + db with a bias)
         self.launches_per_step = ((5 if self.peer is not None else self.plan.launches_per_step - (1 if bias else 0)) + (1 if bias else 0)
@@ -304,6 +305,14 @@ class ShardedHeadPlan:
             if self.world > 1:
                 dist.all_reduce(self.den_global, op=dist.ReduceOp.SUM, group=self.group)
         mark(0)
+        if self.world == 1 and self.fused_step:
+            # one GPU, large batch: the kernels a captured step runs -- forward and dX as ONE kernel, then the dW GEMM
+            p.forward_dx(x, w, y, bias, den=self.den_global)
+            mark(1)
+            p.backward_dw(x, w, den=self.den_global)
+            mark(2)
+            mark(3)
+            return None
         p.forward(x, w, y, bias, want_pred=False, den=self.den_global)
         mark(1)
         p.backward_dw(x, w, den=self.den_global)

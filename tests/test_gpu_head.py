@@ -389,6 +389,8 @@ def test_head_backward_handover_flag_without_a_publishing_forward_falls_back():
     (5000, 512, 600, "garbage", "exact", torch.bfloat16),         # 3 class slices, ragged last row tile, denominator from the label statistics
     (2100, 256, 1000, "entropic", "fast", torch.float32),
     (700, 2048, 152, "softmax", "exact", torch.float32),          # one class slice (no statistics exchange)
+    (9000, 512, 600, "entropic", "exact", torch.bfloat16),        # short mainloops: the MMA warp reaches the dX tiles two epilogues early
+    (16384, 128, 1000, "entropic", "fast", torch.bfloat16),       # two k-blocks per forward tile
 ])
 def test_head_forward_dx_fused_matches_two_kernels(B, K, C, variant, precision, dx_dtype):
     """osb_head_forward_dx runs the forward and the dX GEMM as ONE kernel where the shape allows (every CTA pair goes on
@@ -418,7 +420,7 @@ def test_head_forward_dx_fused_matches_two_kernels(B, K, C, variant, precision, 
     torch.cuda.synchronize()
     outs = lambda: (plan.loss, plan.loss_num, plan.dz, plan.dx, plan.p_target, plan.p_max)
     ref = [t.clone() for t in outs()]
-    for rep in range(3):                          # the launch epoch of the row-tile words advances with every call
+    for rep in range(6):                          # the launch epoch of the row-tile words advances with every call
         for t in outs():
             t.zero_()
         plan.forward_dx(x, w, y, gscale=gs)

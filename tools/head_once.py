@@ -13,7 +13,13 @@ w = (torch.randn(C, K, device=dev) / K ** 0.5).bfloat16()
 y = torch.tensor(O.make_labels(B, C, 1 / 3, seed=1), device=dev)
 from openset_imagenet_b200 import _lib as L
 plan = HeadPlan(B, K, C, device=dev, precision=os.environ.get("OSB_PRECISION", "fast"))
+fused = plan.fused_dx and B > 4096 and os.environ.get("OSB_HEAD_ONCE_UNFUSED") is None
 for _ in range(reps):
-    out = plan.step(x, w, y)
+    if fused:        # the kernels of a captured step at this size: label statistics, forward + dX as one kernel, dW GEMM
+        plan.label_stats(y)
+        plan.forward_dx(x, w, y)
+        plan.backward_dw(x, w)
+    else:
+        plan.step(x, w, y)
 torch.cuda.synchronize()
 print("loss", float(plan.loss[0]) if hasattr(plan, "loss") else "ok")
