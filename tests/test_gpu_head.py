@@ -411,11 +411,13 @@ def test_head_forward_dx_fused_matches_two_kernels(B, K, C, variant, precision, 
     else:
         yn = O.make_labels(B, C, 1 / 3, seed=3)
     y = torch.tensor(yn, device=dev)
-    plan = HeadPlan(B, K, C, variant, **kw)
+    has_bias = C in (300, 600)                    # a bias on three of the cases
+    plan = HeadPlan(B, K, C, variant, bias=has_bias, **kw)
+    bias = (0.5 * torch.randn(C, device=dev, generator=g)) if has_bias else None
     assert plan.fused_dx == (not bool(L.size("osb_head_forward_is_splitk", B, K, C)) and C > 128)
     gs = torch.full((1,), 0.75, device=dev)
     plan.label_stats(y)
-    plan.forward(x, w, y, want_pred=False)
+    plan.forward(x, w, y, bias, want_pred=False)
     plan.backward_dx(x, w, gs)
     torch.cuda.synchronize()
     outs = lambda: (plan.loss, plan.loss_num, plan.dz, plan.dx, plan.p_target, plan.p_max)
@@ -423,7 +425,7 @@ def test_head_forward_dx_fused_matches_two_kernels(B, K, C, variant, precision, 
     for rep in range(6):                          # the launch epoch of the row-tile words advances with every call
         for t in outs():
             t.zero_()
-        plan.forward_dx(x, w, y, gscale=gs)
+        plan.forward_dx(x, w, y, bias, gscale=gs)
         torch.cuda.synchronize()
         for got, want in zip(outs(), ref):
             assert torch.equal(got, want), rep
