@@ -1,20 +1,25 @@
-// Fused open-set head on tcgen05 tensor cores (sm_100a).
+// Fused open-set head on tcgen05 tensor cores (sm_100a).  Every GEMM runs on CTA pairs (cta_group::2, M = 256 MMAs).
 //
-//   head_fwd_kernel : Z = X W^T (+b) accumulated in TMEM, and an epilogue that never writes Z: online
-//                     log-softmax statistics, entropic / softmax / garbage loss, confidence statistics,
-//                     arg-max, and the un-scaled grad-logits dZ (bf16, TMA store).  Heads wider than the
-//                     512 TMEM columns (C <= 1024) run as a 2-CTA cluster that splits the classes and
-//                     exchanges the per-row softmax statistics through distributed shared memory.
-//   head_dx2_kernel : dX = g * dZ W          (persistent, double-buffered TMEM accumulators)
-//   head_dw*_kernel : dW = g * dZ^T X        (split over the batch, deterministic partial reduce)
+//   head_fwd_kernel        : Z = X W^T (+b) accumulated in TMEM (2 x 256 columns, double-buffered), and an epilogue that
+//                            never writes Z: online log-softmax statistics, entropic / softmax / garbage loss, confidence
+//                            statistics, arg-max, and the un-scaled grad-logits dZ (bf16, TMA store).  Persistent; heads
+//                            wider than 256 classes run as a group of up to 4 units (CTA pairs) that share the rows, split
+//                            the classes and exchange the per-row softmax statistics through (value, epoch) words in L2.
+//                            <..., FUSE>: the same kernel goes on with the tiles of the dX GEMM on the same pipeline state.
+//   head_fwd_splitk_kernel : the same for small batches: a cluster of 8 CTAs per 128-row tile, split over K, partial
+//                            logits reduce-scattered through distributed shared memory.
+//   head_dx2_kernel        : dX = g * dZ W          (persistent, double-buffered TMEM accumulators; its three roles are
+//                            the device functions dx_producer / dx_mma / dx_epilogue, shared with the fused kernel)
+//   head_dw2_kernel        : dW = g * dZ^T X        (split over the batch; at most two splits: written by the GEMM itself,
+//                            else fp32 partials + dw_reduce_kernel, deterministic either way); head_dw_kernel: C <= 128
 //
 // dZ is stored DENOMINATOR-FREE, omega_i (p_i - t_i), as one bf16 plane or as two (plane 1 = the bf16 rounding residual of
 // plane 0; the backward GEMMs then run over both planes: K-concatenation, fp32 accumulation); g = gscale / den is applied
 // in the backward epilogues, so the forward kernel never waits for the label statistics.
 //
 // All operands are 128B-swizzled TMA tiles; one tile layout serves as K-major or MN-major operand
-// (tc05.cuh).  Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
-// allocator, warps 2..5 = epilogue (TMEM lane quadrant = warp % 4, one thread per accumulator row).
+// (tc05.cuh).  Warp roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, then the epilogue warps
+// (TMEM lane quadrant = warp % 4): 8 of them (two threads per accumulator row) in the forward and dX kernels, 4 in dW.
 //
 // Reference arithmetic: model.py:23-26,37-38 (linear), losses.py:16-29 / train.py:343,347 (losses),
 // train.py:177 + metrics.py:33-40 + util.py:109-111 (the per-row statistics), autograd of those.
