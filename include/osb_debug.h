@@ -20,6 +20,18 @@ void osb_debug_set_exchange_timeout(long long cycles);    /* same for osb_oscr_e
 void osb_debug_set_curve_trace(void* device_buf);  /* [grid][32] int64 SM clock stamps of oscr_curve_kernel, or NULL */
 void osb_debug_set_records_mode(int bits);         /* stage-A probes: 1 no records emitted, 2 no row loop */
 
+/*
+ * Environment switches read once per process (A/B measurements of launch forms; every variant gives the same bits):
+ *   OSB_NO_PDL=1          no programmatic dependent launches (plain stream order between the kernels of a step)
+ *   OSB_NO_COOP_LAUNCH=1  the persistent forward without the cooperative-launch attribute (Nsight Compute cannot replay
+ *                         a launch that is both cooperative and clustered)
+ *   OSB_NO_DIRECT_DW=1    dW always as split-K partials + reduce kernel, never written by the GEMM itself
+ *   OSB_NO_DW_PREZERO=1   two-split dW by the GEMM as "split 0 stores, split 1 adds after it" even when dX and dW come from one
+ *                         call (default there: dX's kernel clears dW, both splits add)
+ *   OSB_NO_FUSED_DX=1     osb_head_forward_dx always as two kernels
+ *   OSB_NO_ROW_FLAGS=1    OSB_FWD_PUBLISH_ROW_TILES / OSB_BWD_DZ_FROM_PREV_FORWARD are ignored
+ */
+
 #ifdef __cplusplus
 }
 #endif
