@@ -1687,7 +1687,9 @@ static int launch_fwd_k(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
     // (developer switch for Nsight Compute, which fails to replay a launch that is both cooperative and clustered: the
     // grid never exceeds the SM count, so on an otherwise idle GPU all CTAs are resident without the attribute too)
     static const bool no_coop = getenv("OSB_NO_COOP_LAUNCH") != nullptr;
-    if (CL > 1 && !(no_coop && PAIR)) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
+    // (FUSE: every CTA must have read the launch epoch of the row-tile words before the forward's last warp advances it,
+    //  i.e. all CTAs start together -- the same guarantee)
+    if ((CL > 1 || FUSE) && !(no_coop && PAIR)) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
     if (PAIR) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na;
