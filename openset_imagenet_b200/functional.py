@@ -170,9 +170,12 @@ class HeadPlan:
                L.ptr(self.db), 1 if local_reduce else 0, int(flags), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.dev))
 
     def capture(self, x, w, y, bias=None, gscale=None, parallel_backward=None, handover=False, fused_dx=True):
-        """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs the five
-        kernels on the CURRENT CONTENTS of those tensors with a single launch call.  The small-batch configurations
-        (B <= 1024) are bound by launch latency, not by the kernels, so this is the path to use in a training loop."""
+        """Capture one whole step on (x, w, y) into a CUDA graph and return it; ``graph.replay()`` re-runs its kernels
+        (``launches_per_captured_step`` of them: three at the benchmarked shape -- label statistics, forward + dX as one
+        kernel, dW GEMM) on the CURRENT CONTENTS of those tensors with a single launch call.  The small-batch
+        configurations (B <= 1024) are bound by launch latency, not by the kernels, so this is the path to use in a
+        training loop.  ``parallel_backward`` / ``handover`` / ``fused_dx`` override the launch form chosen from the
+        batch size; every form gives the same bits."""
         self._check(x, w, y)
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
@@ -257,7 +260,7 @@ class HeadPlan:
         return graph
 
     def step(self, x, w, y, bias=None, gscale=None, den_scale_hook=None, check=False, want_pred=False):
-        """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd, 5 kernel launches.  A training step
+        """label stats -> fused forward -> dX -> dW (+db): the whole head fwd+bwd as separate launches (4 to 6).  A training step
         has no use for the per-row arg-max / max probability (the reference's train loop reads the loss only,
         train.py:124-139), so they are off unless ``want_pred``; p_target and p_max are always written."""
         if check:
