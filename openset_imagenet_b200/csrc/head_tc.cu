@@ -1654,6 +1654,8 @@ static int dw_splits(int B, int K, int C) {
     if (s < 1) s = 1;
     if (s > 16) s = 16;
     if (s > kb_total) s = kb_total < 1 ? 1 : kb_total;
+    // (two splits for small batches too, so that the GEMM writes dW itself, were measured at the BG configuration, 1024 x 2048
+    //  -> 152: 33.2 -> 32.6 us per step on one GPU, 56.6 us unchanged on two: not adopted)
     return s;
 }
 
